@@ -1,0 +1,1035 @@
+// am_engine.cu -- host driver + C ABI of the B200-native Analytic Marching engine.
+//
+// Replaces reference backend/src/cuam_kernel.cu (global singleton, host-driven LIFO loop with
+// O(100-1000) launches and blocking scalar copies per batch of 1024 states) by a handle-based,
+// level-synchronous BFS that keeps the frontier, the visited set and the mesh on the device and
+// synchronises with the host once per BFS level (one 16-byte read-back of the counters).
+//
+// Per level [lb, le):   for each chunk of states
+//                           compose (one FP64 GEMM launch per hidden layer, compose.cuh)
+//                           level plane (equ_kernel), clip (clip.cuh), scan + compact faces
+//                       expand + insert (frontier.cuh phase 1), count winners, scan,
+//                       -> read back n_new, grow arenas, finalize (phase 2)
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/am_b200.h"
+#include "clip.cuh"
+#include "common.cuh"
+#include "compose.cuh"
+#include "frontier.cuh"
+#include "mesh.cuh"
+
+using namespace amb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaFail {
+    std::string msg;
+};
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            throw CudaFail{std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                           std::to_string(__LINE__) + ")"};                                               \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+    // grow to at least `bytes`; keeps the first `keep` bytes
+    void reserve(size_t bytes, size_t keep = 0, bool geometric = true)
+    {
+        if (bytes <= cap) return;
+        size_t want = bytes;
+        if (geometric && cap) want = std::max(bytes, cap * 2);
+        void *np = nullptr;
+        if (p) CK(cudaDeviceSynchronize());   // in-flight kernels on the engine stream may still use `p`
+        CK(cudaMalloc(&np, want));
+        if (p && keep) CK(cudaMemcpy(np, p, std::min(keep, cap), cudaMemcpyDeviceToDevice));
+        if (p) CK(cudaFree(p));
+        p = np;
+        cap = want;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Skip {
+    int src;        // 0 = raw input, j >= 1 = hidden layer j
+    int tm;         // transform index
+};
+
+int pow2_group(int kw4)
+{
+    int g = 1;
+    while (g < kw4 && g < 32) g <<= 1;
+    return g;
+}
+
+}  // namespace
+
+struct am_handle {
+    bool f64 = true;
+    int D = 0;
+    std::vector<int> n;          // n[0]=3 .. n[D+1]=1
+    std::vector<int> off;        // off[h], h=1..D ; off[D+1] = L
+    int L = 0, E = 0, kw = 0, kw4 = 0, n1 = 0, R = 0, G = 1;
+    std::vector<std::vector<Skip>> skips;   // per fc layer h = 1..D (index h)
+    int n_tm = 0;
+
+    // ---- network on the device (double) ----
+    std::vector<DevBuf> Wt, bias;           // index h = 1..D-1 (hidden -> hidden)
+    std::vector<int> Mpad, Kpad;
+    DevBuf P1, wout, extra;
+    double bout = 0.0;
+    std::vector<DevBuf> TM, TMt;            // row-major (out,in) and k-major padded copies
+    std::vector<int> tm_h, tm_w, tm_Mpad;
+    bool weights_loaded = false;
+
+    // ---- state arena ----
+    DevBuf keys, hsum, parent, via, seedpt, face_off;
+    size_t cap_states = 0;
+    DevBuf face_edges, face_xyz;
+    size_t cap_corners = 0;
+    DevBuf table;
+    uint32_t tcap = 0;
+    long long n_states = 0;
+    std::vector<long long> level_begin;
+
+    // ---- scratch ----
+    DevBuf planes, equ, f_cnt, f_off, f_edges, f_verts, cand_slot, nwin, wbase, scan_a, scan_b, counters;
+    DevBuf xkeys, xh, xpt, xslot, xstates;
+    unsigned long long *h_counters = nullptr;   // pinned
+    cudaStream_t stream = nullptr;
+
+    // ---- results ----
+    bool has_march = false, has_mesh = false;
+    am_stats stats{};
+    std::vector<double> h_vertices;
+    std::vector<int> h_corner_vid;
+    std::vector<long long> h_face_off;
+    double gemm_ms = 0.0, gemm_flops = 0.0;
+    long long gemm_launches = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { size_t a, b; int kind; double flops; };
+    std::vector<Span> spans;
+    std::string err;
+
+    // ------------------------------------------------------------------------------------------
+    cudaEvent_t ev()
+    {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            ev_pool.push_back(e);
+        }
+        cudaEvent_t e = ev_pool[ev_used++];
+        CK(cudaEventRecord(e, stream));
+        return e;
+    }
+    bool timing_on() const { return ev_used < 60000; }
+    size_t span_begin() { ev(); return ev_used - 1; }
+    void span_end(size_t a, int kind, double flops = 0.0)
+    {
+        ev();
+        spans.push_back(Span{a, ev_used - 1, kind, flops});
+    }
+
+    void free_all()
+    {
+        for (auto &b : Wt) b.release();
+        for (auto &b : bias) b.release();
+        for (auto &b : TM) b.release();
+        for (auto &b : TMt) b.release();
+        DevBuf *all[] = {&P1, &wout, &extra, &keys, &hsum, &parent, &via, &seedpt, &face_off, &face_edges, &face_xyz,
+                         &table, &planes, &equ, &f_cnt, &f_off, &f_edges, &f_verts, &cand_slot, &nwin, &wbase, &scan_a,
+                         &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates};
+        for (DevBuf *b : all) b->release();
+        for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+        ev_pool.clear();
+        if (h_counters) cudaFreeHost(h_counters);
+        h_counters = nullptr;
+    }
+
+    // rows of hidden layer h for state 0 of a chunk + stride (doubles)
+    const double *layer_rows(int h, long long *stride) const
+    {
+        if (h == 1) {
+            *stride = 0;
+            return P1.as<double>();
+        }
+        *stride = 4LL * R;
+        return planes.as<double>() + 4LL * (off[h] - n1);
+    }
+
+    void ensure_states(size_t want)
+    {
+        if (want <= cap_states) return;
+        size_t ncap = std::max<size_t>(want, std::max<size_t>(cap_states * 2, 1 << 14));
+        const size_t keep = (size_t)n_states;
+        keys.reserve(ncap * kw * 4, keep * kw * 4, false);
+        hsum.reserve(ncap * 8, keep * 8, false);
+        parent.reserve(ncap * 4, keep * 4, false);
+        via.reserve(ncap * 4, keep * 4, false);
+        seedpt.reserve(ncap * 24, keep * 24, false);
+        face_off.reserve((ncap + 1) * 8, (keep + 1) * 8, false);
+        cap_states = ncap;
+    }
+    void ensure_corners(size_t want, size_t keep)
+    {
+        if (want <= cap_corners) return;
+        size_t ncap = std::max<size_t>(want, std::max<size_t>(cap_corners * 2, 1 << 16));
+        face_edges.reserve(ncap * 4, keep * 4, false);
+        face_xyz.reserve(ncap * 24, keep * 24, false);
+        cap_corners = ncap;
+    }
+    void ensure_table(size_t entries)
+    {
+        uint32_t want = 1u << 12;
+        while ((size_t)want < entries * 2) want <<= 1;
+        if (want <= tcap) return;
+        table.reserve((size_t)want * 8, 0, false);
+        tcap = want;
+        CK(cudaMemsetAsync(table.p, 0xFF, (size_t)tcap * 8, stream));
+        if (n_states > 0) {
+            TableRef t{table.as<unsigned long long>(), tcap - 1};
+            rehash_kernel<<<(unsigned)((n_states + 255) / 256), 256, 0, stream>>>(hsum.as<unsigned long long>(),
+                                                                                 (int)n_states, t);
+            CK(cudaGetLastError());
+        }
+    }
+
+    // exclusive scan of n uint32 -> out ; total (64-bit) written to *total_dev if not null
+    void scan(const uint32_t *in, uint32_t *out, int n, unsigned long long *total_dev)
+    {
+        if (n <= 0) {
+            if (total_dev) CK(cudaMemsetAsync(total_dev, 0, 8, stream));
+            return;
+        }
+        const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+        if (nb == 1) {
+            scan_apply_kernel<<<1, SCAN_THREADS, 0, stream>>>(in, n, nullptr, out, total_dev);
+            CK(cudaGetLastError());
+            return;
+        }
+        scan_a.reserve((size_t)nb * 4);
+        scan_b.reserve((size_t)nb * 4 + (size_t)((nb + SCAN_TILE - 1) / SCAN_TILE) * 8 + 64);
+        scan_reduce_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_a.as<uint32_t>());
+        CK(cudaGetLastError());
+        if (nb <= SCAN_TILE) {
+            scan_apply_kernel<<<1, SCAN_THREADS, 0, stream>>>(scan_a.as<uint32_t>(), nb, nullptr, scan_b.as<uint32_t>(),
+                                                            nullptr);
+        } else {  // three levels: up to SCAN_TILE^3 items
+            const int nb2 = (nb + SCAN_TILE - 1) / SCAN_TILE;
+            uint32_t *l2 = scan_b.as<uint32_t>() + nb;
+            scan_reduce_kernel<<<nb2, SCAN_THREADS, 0, stream>>>(scan_a.as<uint32_t>(), nb, l2);
+            scan_apply_kernel<<<1, SCAN_THREADS, 0, stream>>>(l2, nb2, nullptr, l2 + nb2, nullptr);
+            scan_apply_kernel<<<nb2, SCAN_THREADS, 0, stream>>>(scan_a.as<uint32_t>(), nb, l2 + nb2,
+                                                              scan_b.as<uint32_t>(), nullptr);
+        }
+        CK(cudaGetLastError());
+        scan_apply_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_b.as<uint32_t>(), out, total_dev);
+        CK(cudaGetLastError());
+    }
+
+    // ---------------- composition of one chunk: keys of states [sid0, sid0+Sc) -------------------
+    void launch_gemm(const double *Wt_, int Mpad_, int M, int K, const double *Bsrc, long long bstride, int bit0,
+                     double *out, const double *bias_, const uint32_t *keys0, int Sc, int accumulate)
+    {
+        GemmArgs g{};
+        g.Wt = Wt_; g.Mpad = Mpad_; g.M = M; g.K = K;
+        g.Bsrc = Bsrc; g.b_stride = bstride;
+        g.keys = keys0; g.kw = kw; g.bit0 = bit0;
+        g.out = out; g.out_stride = 4LL * R;
+        g.bias = bias_; g.S = Sc; g.accumulate = accumulate;
+        dim3 grid(Mpad_ / GM_BM, (Sc + GM_BS - 1) / GM_BS);
+        const double flops = 2.0 * M * (double)K * 4.0 * Sc;
+        const bool t = timing_on();
+        size_t a = 0;
+        if (t) a = span_begin();
+        compose_gemm_kernel<<<grid, GM_THREADS, GM_SMEM_BYTES, stream>>>(g);
+        CK(cudaGetLastError());
+        if (t) span_end(a, 0, flops);
+        stats.compose_flops += flops;
+    }
+
+    void compose_chunk(const uint32_t *keys0, int Sc, double iso)
+    {
+        for (int h = 1; h < D; ++h) {   // fc layer h: hidden h -> hidden h+1
+            long long bstride;
+            const double *Bsrc = layer_rows(h, &bstride);
+            double *out = planes.as<double>() + 4LL * (off[h + 1] - n1);
+            launch_gemm(Wt[h].as<double>(), Mpad[h], n[h + 1], n[h], Bsrc, bstride, off[h], out, bias[h].as<double>(),
+                        keys0, Sc, 0);
+            for (const Skip &sk : skips[h]) {
+                const bool identity = (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0);
+                const int M = n[h + 1];
+                if (sk.src == 0) {
+                    const long long tot = (long long)Sc * M;
+                    skip_input_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+                        out, 4LL * R, M, Sc, identity ? nullptr : TM[sk.tm].as<double>());
+                } else {
+                    long long sstride;
+                    const double *src = layer_rows(sk.src, &sstride);
+                    if (identity) {
+                        const long long tot = (long long)Sc * M * 4;
+                        skip_hidden_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+                            out, 4LL * R, src, sstride, keys0, kw, off[sk.src], M, Sc);
+                    } else {
+                        launch_gemm(TMt[sk.tm].as<double>(), tm_Mpad[sk.tm], M, n[sk.src], src, sstride, off[sk.src],
+                                    out, nullptr, keys0, Sc, 1);
+                    }
+                }
+                CK(cudaGetLastError());
+            }
+        }
+        EquArgs e{};
+        e.w = wout.as<double>();
+        e.bias = bout;
+        e.iso = iso;
+        e.in = layer_rows(D, &e.in_stride);
+        e.keys = keys0; e.kw = kw; e.bit0 = off[D]; e.K = n[D]; e.S = Sc;
+        e.equ = equ.as<double>();
+        e.n_skips = 0;
+        for (const Skip &sk : skips[D]) {
+            if (e.n_skips == EQU_MAX_SKIPS) throw CudaFail{"more than 4 skips into the output layer"};
+            EquSkip &q = e.skips[e.n_skips++];
+            const bool identity = (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0);
+            q.T = identity ? nullptr : TM[sk.tm].as<double>();
+            q.src = nullptr; q.src_stride = 0; q.src_bit0 = 0; q.src_n = 0;
+            if (sk.src == 0) {
+                q.kind = identity ? 1 : 2;
+            } else {
+                q.kind = identity ? 3 : 4;
+                q.src = layer_rows(sk.src, &q.src_stride);
+                q.src_bit0 = off[sk.src];
+                q.src_n = n[sk.src];
+            }
+        }
+        equ_kernel<<<(Sc * 4 + 127) / 128, 128, 0, stream>>>(e);
+        CK(cudaGetLastError());
+    }
+
+    size_t chunk_states() const
+    {
+        double gib = 8.0;
+        if (const char *s = getenv("AM_B200_PLANE_GIB")) gib = atof(s);
+        const size_t per = std::max<size_t>((size_t)R * 32, 32);
+        size_t c = (size_t)(gib * (1ull << 30)) / per;
+        c = std::max<size_t>(c, 1024);
+        c = std::min<size_t>(c, 1u << 22);
+        return (c / GM_BS) * GM_BS;
+    }
+
+    void ensure_chunk_scratch(size_t Sc)
+    {
+        planes.reserve(std::max<size_t>((size_t)R * 32 * Sc, 64), 0, false);
+        equ.reserve(Sc * 32, 0, false);
+        f_cnt.reserve(Sc * 4, 0, false);
+        f_off.reserve(Sc * 4, 0, false);
+        f_edges.reserve(Sc * VSLOTS * 4, 0, false);
+        f_verts.reserve(Sc * VSLOTS * 24, 0, false);
+    }
+
+    void read_counters()
+    {
+        CK(cudaMemcpyAsync(h_counters, counters.p, CNT_NUM * 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    template <typename F>
+    void dispatch_group(F &&f)
+    {
+        switch (G) {
+            case 1: f(std::integral_constant<int, 1>{}); break;
+            case 2: f(std::integral_constant<int, 2>{}); break;
+            case 4: f(std::integral_constant<int, 4>{}); break;
+            case 8: f(std::integral_constant<int, 8>{}); break;
+            case 16: f(std::integral_constant<int, 16>{}); break;
+            default: f(std::integral_constant<int, 32>{}); break;
+        }
+    }
+};
+
+// =================================================================================================
+namespace {
+
+enum PtrKind { PK_HOST, PK_DEVICE };
+PtrKind classify(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return PK_HOST;
+    }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? PK_DEVICE : PK_HOST;
+}
+
+// fetch `count` reals (float or double, host or device) as doubles on the host
+std::vector<double> fetch_real(const void *p, size_t count, bool f64)
+{
+    std::vector<double> out(count);
+    if (count == 0) return out;
+    if (p == nullptr) throw CudaFail{"null data pointer"};
+    const size_t es = f64 ? 8 : 4;
+    std::vector<unsigned char> tmp;
+    const void *src = p;
+    if (classify(p) == PK_DEVICE) {
+        tmp.resize(count * es);
+        CK(cudaMemcpy(tmp.data(), p, count * es, cudaMemcpyDeviceToHost));
+        src = tmp.data();
+    }
+    if (f64) memcpy(out.data(), src, count * 8);
+    else for (size_t i = 0; i < count; ++i) out[i] = (double)static_cast<const float *>(src)[i];
+    return out;
+}
+
+void upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st)
+{
+    b.reserve(std::max<size_t>(bytes, 16), 0, false);
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+}
+
+int load_weights(am_handle *h, const void *const *W, const void *const *B, const void *const *TMp, const int *tm_shapes,
+                 int n_tm)
+{
+    const int D = h->D;
+    if (n_tm < h->n_tm) throw CudaFail{"arc_table references transform " + std::to_string(h->n_tm - 1) +
+                                       " but only " + std::to_string(n_tm) + " were given"};
+    // layer 0 -> shared table of hidden layer 1 rows
+    {
+        auto w0 = fetch_real(W[0], (size_t)h->n1 * 3, h->f64);
+        auto b0 = fetch_real(B[0], (size_t)h->n1, h->f64);
+        std::vector<double> p1((size_t)h->n1 * 4);
+        for (int r = 0; r < h->n1; ++r) {
+            p1[4 * r + 0] = w0[3 * r + 0]; p1[4 * r + 1] = w0[3 * r + 1]; p1[4 * r + 2] = w0[3 * r + 2];
+            p1[4 * r + 3] = b0[r];
+        }
+        upload(h->P1, p1.data(), p1.size() * 8, h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    for (int l = 1; l < D; ++l) {
+        const int K = h->n[l], M = h->n[l + 1];
+        const int Kp = (K + GM_BK - 1) / GM_BK * GM_BK, Mp = (M + GM_BM - 1) / GM_BM * GM_BM;
+        h->Kpad[l] = Kp; h->Mpad[l] = Mp;
+        auto w = fetch_real(W[l], (size_t)M * K, h->f64);
+        auto b = fetch_real(B[l], (size_t)M, h->f64);
+        std::vector<double> wt((size_t)Kp * Mp, 0.0);
+        for (int m = 0; m < M; ++m)
+            for (int k = 0; k < K; ++k) wt[(size_t)k * Mp + m] = w[(size_t)m * K + k];
+        upload(h->Wt[l], wt.data(), wt.size() * 8, h->stream);
+        upload(h->bias[l], b.data(), b.size() * 8, h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    {
+        auto w = fetch_real(W[D], (size_t)h->n[D], h->f64);
+        auto b = fetch_real(B[D], 1, h->f64);
+        upload(h->wout, w.data(), w.size() * 8, h->stream);
+        h->bout = b[0];
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->TM.resize(n_tm); h->TMt.resize(n_tm);
+    h->tm_h.assign(n_tm, 0); h->tm_w.assign(n_tm, 0); h->tm_Mpad.assign(n_tm, 0);
+    for (int t = 0; t < n_tm; ++t) {
+        const int th = tm_shapes[2 * t], tw = tm_shapes[2 * t + 1];
+        h->tm_h[t] = th; h->tm_w[t] = tw;
+        if (th == 0 && tw == 0) continue;
+        auto w = fetch_real(TMp[t], (size_t)th * tw, h->f64);
+        upload(h->TM[t], w.data(), w.size() * 8, h->stream);
+        const int Kp = (tw + GM_BK - 1) / GM_BK * GM_BK, Mp = (th + GM_BM - 1) / GM_BM * GM_BM;
+        h->tm_Mpad[t] = Mp;
+        std::vector<double> wt((size_t)Kp * Mp, 0.0);
+        for (int m = 0; m < th; ++m)
+            for (int k = 0; k < tw; ++k) wt[(size_t)k * Mp + m] = w[(size_t)m * tw + k];
+        upload(h->TMt[t], wt.data(), wt.size() * 8, h->stream);
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    // shape checks of the skips (reference backend/src/cuam.cpp:153-173)
+    for (int l = 1; l <= D; ++l)
+        for (const Skip &sk : h->skips[l]) {
+            const int th = h->tm_h[sk.tm], tw = h->tm_w[sk.tm];
+            const int src_w = (sk.src == 0) ? 3 : h->n[sk.src];
+            if (th == 0 && tw == 0) {
+                if (src_w != h->n[l + 1] && !(sk.src == 0 && h->n[l + 1] <= 3))
+                    throw CudaFail{"identity skip between layers of different width"};
+            } else if (th != h->n[l + 1] || tw != src_w) {
+                throw CudaFail{"transform " + std::to_string(sk.tm) + " has shape (" + std::to_string(th) + "," +
+                               std::to_string(tw) + "), expected (" + std::to_string(h->n[l + 1]) + "," +
+                               std::to_string(src_w) + ")"};
+            }
+        }
+    h->weights_loaded = true;
+    return AM_OK;
+}
+
+void insert_seeds(am_handle *h, const uint8_t *states, const double *points, long long N)
+{
+    cudaStream_t st = h->stream;
+    h->xstates.reserve((size_t)N * h->L, 0, false);
+    if (classify(states) == PK_DEVICE)
+        CK(cudaMemcpyAsync(h->xstates.p, states, (size_t)N * h->L, cudaMemcpyDeviceToDevice, st));
+    else
+        CK(cudaMemcpyAsync(h->xstates.p, states, (size_t)N * h->L, cudaMemcpyHostToDevice, st));
+    h->xkeys.reserve((size_t)N * h->kw * 4, 0, false);
+    h->xh.reserve((size_t)N * 8, 0, false);
+    h->xslot.reserve((size_t)N * 4, 0, false);
+    upload(h->xpt, points, (size_t)N * 24, st);
+    h->nwin.reserve((size_t)N * 4, 0, false);
+    h->wbase.reserve((size_t)N * 4, 0, false);
+    const long long tot = N * h->kw;
+    pack_states_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->xstates.as<uint8_t>(), (int)N, h->L, h->kw,
+                                                                     h->xkeys.as<uint32_t>());
+    hash_keys_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->xkeys.as<uint32_t>(), (int)N, h->kw,
+                                                                 h->xh.as<unsigned long long>());
+    CK(cudaGetLastError());
+    h->ensure_table((size_t)h->n_states + (size_t)N);
+    h->ensure_states((size_t)h->n_states + (size_t)N);
+    XArgs x{};
+    x.xkeys = h->xkeys.as<uint32_t>(); x.xh = h->xh.as<unsigned long long>(); x.xpt = h->xpt.as<double>();
+    x.xparent = nullptr; x.xvia = nullptr;
+    x.N = (int)N; x.kw = h->kw; x.kw4 = h->kw4;
+    x.keys = h->keys.as<uint32_t>();
+    x.table = TableRef{h->table.as<unsigned long long>(), h->tcap - 1};
+    x.x_slot = h->xslot.as<int>(); x.xwin = h->nwin.as<uint32_t>(); x.win_base = h->wbase.as<uint32_t>();
+    x.keys_w = h->keys.as<uint32_t>(); x.hsum_w = h->hsum.as<unsigned long long>();
+    x.parent = h->parent.as<int>(); x.via_edge = h->via.as<int>(); x.seedpt = h->seedpt.as<double>();
+    x.n_states = (int)h->n_states;
+    const int G = h->G;
+    const unsigned gb = (unsigned)((N * G + 255) / 256);
+    h->dispatch_group([&](auto g) { x_insert_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(x); });
+    x_count_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x);
+    CK(cudaGetLastError());
+    h->scan(h->nwin.as<uint32_t>(), h->wbase.as<uint32_t>(), (int)N, h->counters.as<unsigned long long>() + CNT_NEW);
+    h->dispatch_group([&](auto g) { x_finalize_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(x); });
+    CK(cudaGetLastError());
+    h->read_counters();
+    h->n_states += (long long)h->h_counters[CNT_NEW];
+}
+
+void process_level(am_handle *h, long long lb, long long le, double iso, int flip)
+{
+    cudaStream_t st = h->stream;
+    const long long S = le - lb;
+    const size_t chunk = h->chunk_states();
+    unsigned long long *cnt = h->counters.as<unsigned long long>();
+    long long corners_upper = (long long)h->h_counters[CNT_CORNERS];
+    for (long long c0 = 0; c0 < S; c0 += (long long)chunk) {
+        const int Sc = (int)std::min<long long>((long long)chunk, S - c0);
+        const long long sid0 = lb + c0;
+        h->ensure_chunk_scratch((size_t)Sc);
+        h->ensure_corners((size_t)(corners_upper + (long long)Sc * VSLOTS), (size_t)corners_upper);
+        const uint32_t *keys0 = h->keys.as<uint32_t>() + (size_t)sid0 * h->kw;
+
+        size_t t0 = 0;
+        const bool timing = h->timing_on();
+        if (timing) t0 = h->span_begin();
+        h->compose_chunk(keys0, Sc, iso);
+        if (timing) h->span_end(t0, 1);
+
+        if (timing) t0 = h->span_begin();
+        ClipArgs ca{};
+        ca.keys = keys0; ca.kw = h->kw;
+        ca.P1 = h->P1.as<double>(); ca.n1 = h->n1;
+        ca.P = h->planes.as<double>(); ca.p_stride = 4LL * h->R;
+        ca.equ = h->equ.as<double>();
+        ca.extra = h->extra.as<double>();
+        ca.L = h->L; ca.E = h->E; ca.S = Sc; ca.flip = flip;
+        ca.seedpt = h->seedpt.as<double>() + (size_t)sid0 * 3;
+        ca.out_cnt = h->f_cnt.as<int>(); ca.out_edges = h->f_edges.as<int>(); ca.out_verts = h->f_verts.as<double>();
+        ca.counters = cnt;
+        clip_kernel<<<(Sc + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, 0, st>>>(ca);
+        CK(cudaGetLastError());
+        h->scan(h->f_cnt.as<uint32_t>(), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
+        CompactArgs co{};
+        co.cnt = h->f_cnt.as<int>(); co.off = h->f_off.as<uint32_t>();
+        co.edges = h->f_edges.as<int>(); co.verts = h->f_verts.as<double>();
+        co.S = Sc; co.sid0 = (int)sid0;
+        co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
+        co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
+        compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
+        bump_counters_kernel<<<1, 256, 0, st>>>(cnt, h->f_cnt.as<int>(), Sc);
+        CK(cudaGetLastError());
+        if (timing) h->span_end(t0, 2);
+        corners_upper += (long long)Sc * VSLOTS;
+    }
+
+    // ---- neighbour enumeration + visited set ----------------------------------------------------
+    size_t t0 = 0;
+    const bool timing = h->timing_on();
+    if (timing) t0 = h->span_begin();
+    h->ensure_table((size_t)h->n_states + (size_t)S * VSLOTS);
+    h->cand_slot.reserve((size_t)S * VSLOTS * 4, 0, false);
+    h->nwin.reserve((size_t)S * 4, 0, false);
+    h->wbase.reserve((size_t)S * 4, 0, false);
+    LevelArgs a{};
+    a.keys = h->keys.as<uint32_t>(); a.hsum = h->hsum.as<unsigned long long>();
+    a.face_off = h->face_off.as<long long>(); a.face_edges = h->face_edges.as<int>();
+    a.face_xyz = h->face_xyz.as<double>();
+    a.kw = h->kw; a.kw4 = h->kw4; a.L = h->L; a.lb = (int)lb; a.S = (int)S;
+    a.table = TableRef{h->table.as<unsigned long long>(), h->tcap - 1};
+    a.cand_slot = h->cand_slot.as<int>(); a.nwin = h->nwin.as<uint32_t>(); a.win_base = h->wbase.as<uint32_t>();
+    a.counters = cnt;
+    const int G = h->G;
+    const unsigned gb = (unsigned)((S * G + 255) / 256);
+    h->dispatch_group([&](auto g) { expand_insert_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
+    count_winners_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+    h->scan(h->nwin.as<uint32_t>(), h->wbase.as<uint32_t>(), (int)S, cnt + CNT_NEW);
+    h->read_counters();                                   // the one host sync of the level
+    const long long n_new = (long long)h->h_counters[CNT_NEW];
+    if (h->n_states + n_new >= (1LL << 31) - 1) throw CudaFail{"more than 2^31 states"};
+    h->ensure_states((size_t)(h->n_states + n_new));
+    a.keys = h->keys.as<uint32_t>(); a.hsum = h->hsum.as<unsigned long long>();   // arenas may have moved
+    a.face_off = h->face_off.as<long long>();
+    a.keys_w = h->keys.as<uint32_t>(); a.hsum_w = h->hsum.as<unsigned long long>();
+    a.parent = h->parent.as<int>(); a.via_edge = h->via.as<int>(); a.seedpt = h->seedpt.as<double>();
+    a.n_states = (int)h->n_states;
+    if (n_new > 0) {
+        h->dispatch_group([&](auto g) { finalize_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
+        CK(cudaGetLastError());
+    }
+    if (timing) h->span_end(t0, 3);
+    h->n_states += n_new;
+}
+
+void resolve_spans(am_handle *h)
+{
+    double ms_k[4] = {0, 0, 0, 0};
+    h->gemm_ms = 0; h->gemm_flops = 0; h->gemm_launches = 0;
+    for (const auto &s : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[s.a], h->ev_pool[s.b]) != cudaSuccess) { cudaGetLastError(); continue; }
+        ms_k[s.kind] += ms;
+        if (s.kind == 0) { h->gemm_flops += s.flops; h->gemm_launches++; }
+    }
+    h->gemm_ms = ms_k[0];
+    h->stats.seconds_compose = ms_k[1] * 1e-3;
+    h->stats.seconds_clip = ms_k[2] * 1e-3;
+    h->stats.seconds_frontier = ms_k[3] * 1e-3;
+}
+
+}  // namespace
+
+// =================================================================================================
+//                                           C ABI
+// =================================================================================================
+extern "C" {
+
+const char *am_last_error(const am_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const int *arc_table, int arc_rows,
+              int arc_cols, int num_extra_constraints)
+{
+    g_create_error.clear();
+    if (!out || !nodes || n_nodes < 3 || nodes[0] != 3 || nodes[n_nodes - 1] != 1 || num_extra_constraints < 0 ||
+        arc_rows != n_nodes - 2 || (arc_rows > 0 && (!arc_table || arc_cols < 1 || (arc_cols + 1) % 2 != 0))) {
+        g_create_error = "am_create: malformed architecture (need nodes = [3, ..., 1], one arc_table row per hidden "
+                         "layer, an odd number of arc_table columns, num_extra_constraints >= 0)";
+        return AM_ERR_ARG;
+    }
+    am_handle *h = new am_handle();
+    try {
+        h->f64 = is_f64 != 0;
+        h->D = n_nodes - 2;
+        h->n.assign(nodes, nodes + n_nodes);
+        for (int v : h->n)
+            if (v <= 0) throw CudaFail{"non-positive layer width"};
+        h->off.assign(h->D + 2, 0);
+        for (int l = 1; l <= h->D; ++l) h->off[l + 1] = h->off[l] + h->n[l];
+        h->L = h->off[h->D + 1];
+        h->E = num_extra_constraints;
+        h->kw4 = (h->L + 127) / 128;
+        h->kw = 4 * h->kw4;
+        h->n1 = h->n[1];
+        h->R = h->L - h->n1;
+        h->G = pow2_group(h->kw4);
+        h->skips.assign(h->D + 1, {});
+        h->n_tm = 0;
+        for (int r = 0; r < arc_rows; ++r) {
+            const int *row = arc_table + (size_t)r * arc_cols;
+            if (row[0] < 0 || 1 + 2 * row[0] > arc_cols) throw CudaFail{"arc_table row " + std::to_string(r) + " is too short"};
+            for (int j = 0; j < row[0]; ++j) {
+                Skip sk{row[1 + 2 * j], row[2 + 2 * j]};
+                if (sk.src < 0 || sk.src > r + 1 || sk.tm < 0)
+                    throw CudaFail{"arc_table row " + std::to_string(r) + ": bad source/transform index"};
+                h->skips[r + 1].push_back(sk);
+                h->n_tm = std::max(h->n_tm, sk.tm + 1);
+            }
+        }
+        h->Wt.resize(h->D + 1); h->bias.resize(h->D + 1);
+        h->Mpad.assign(h->D + 1, 0); h->Kpad.assign(h->D + 1, 0);
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(cudaMallocHost(&h->h_counters, CNT_NUM * 8));
+        memset(h->h_counters, 0, CNT_NUM * 8);
+        h->counters.reserve(CNT_NUM * 8);
+        CK(cudaFuncSetAttribute(compose_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM_BYTES));
+    } catch (const CudaFail &f) {
+        g_create_error = "am_create: " + f.msg;
+        h->free_all();
+        if (h->stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return AM_ERR_CUDA;
+    }
+    *out = h;
+    return AM_OK;
+}
+
+void am_destroy(am_handle *h)
+{
+    if (!h) return;
+    h->free_all();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int am_load_weights(am_handle *h, const void *const *W, const void *const *B, const void *const *TM, const int *tm_shapes,
+                    int n_tm)
+{
+    if (!h || !W || !B || (n_tm > 0 && (!TM || !tm_shapes))) {
+        if (h) h->err = "am_load_weights: null argument";
+        return AM_ERR_ARG;
+    }
+    try {
+        return load_weights(h, W, B, TM, tm_shapes, n_tm);
+    } catch (const CudaFail &f) {
+        h->err = "am_load_weights: " + f.msg;
+        return AM_ERR_CUDA;
+    }
+}
+
+int am_march(am_handle *h, const void *const *W, const void *const *B, const void *const *TM, const int *tm_shapes,
+             int n_tm, const uint8_t *states, const void *points, int64_t n_seeds, const void *w_extra,
+             const void *b_extra, int n_extra, double iso, int flip_insideout, void *user_stream)
+{
+    if (!h) return AM_ERR_ARG;
+    if (!W || !B || !states || !points || n_seeds < 1 || (n_tm > 0 && (!TM || !tm_shapes))) {
+        h->err = "am_march: null argument or no seed states";
+        return AM_ERR_ARG;
+    }
+    if (n_extra != h->E) {
+        h->err = "am_march: " + std::to_string(n_extra) + " extra constraints given but the environment was created for " +
+                 std::to_string(h->E);
+        return AM_ERR_ARG;
+    }
+    h->has_march = false;
+    h->has_mesh = false;
+    try {
+        cudaStream_t st = h->stream;
+        if (user_stream) {   // order after the caller's stream
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CK(cudaEventRecord(e, (cudaStream_t)user_stream));
+            CK(cudaStreamWaitEvent(st, e, 0));
+            CK(cudaEventDestroy(e));
+        } else {
+            CK(cudaDeviceSynchronize());
+        }
+        h->ev_used = 0;
+        h->spans.clear();
+        h->stats = am_stats{};
+        cudaEvent_t e_begin = h->ev();
+        load_weights(h, W, B, TM, tm_shapes, n_tm);
+        {
+            auto we = fetch_real(w_extra, (size_t)h->E * 3, h->f64);
+            auto be = fetch_real(b_extra, (size_t)h->E, h->f64);
+            std::vector<double> ex((size_t)h->E * 4 + 4, 0.0);
+            for (int e = 0; e < h->E; ++e) {
+                ex[4 * e + 0] = we[3 * e + 0]; ex[4 * e + 1] = we[3 * e + 1]; ex[4 * e + 2] = we[3 * e + 2];
+                ex[4 * e + 3] = be[e];
+            }
+            upload(h->extra, ex.data(), ex.size() * 8, st);
+            CK(cudaStreamSynchronize(st));
+        }
+        auto pts = fetch_real(points, (size_t)n_seeds * 3, h->f64);
+        h->n_states = 0;
+        h->level_begin.clear();
+        CK(cudaMemsetAsync(h->counters.p, 0, CNT_NUM * 8, st));
+        memset(h->h_counters, 0, CNT_NUM * 8);
+        if (h->tcap) CK(cudaMemsetAsync(h->table.p, 0xFF, (size_t)h->tcap * 8, st));
+        insert_seeds(h, states, pts.data(), n_seeds);
+        h->stats.n_seeds = n_seeds;
+        h->stats.n_unique_seeds = h->n_states;
+        long long lb = 0, le = h->n_states;
+        while (le > lb) {
+            h->level_begin.push_back(lb);
+            h->stats.max_level_states = std::max<int64_t>(h->stats.max_level_states, le - lb);
+            process_level(h, lb, le, iso, flip_insideout);
+            lb = le;
+            le = h->n_states;
+        }
+        h->level_begin.push_back(h->n_states);
+        cudaEvent_t e_end = h->ev();
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e_begin, e_end));
+        h->read_counters();
+        resolve_spans(h);
+        am_stats &s = h->stats;
+        s.seconds_march = ms * 1e-3;
+        s.n_states = h->n_states;
+        s.n_faces = (int64_t)h->h_counters[CNT_FACES];
+        s.n_corners = (int64_t)h->h_counters[CNT_CORNERS];
+        s.n_levels = (int64_t)h->level_begin.size() - 1;
+        s.n_candidates = (int64_t)h->h_counters[CNT_CANDIDATES];
+        s.n_unbounded = (int64_t)h->h_counters[CNT_UNBOUNDED];
+        s.n_overflow = (int64_t)h->h_counters[CNT_OVERFLOW];
+        s.n_over_vertmax = (int64_t)h->h_counters[CNT_OVER_VERTMAX];
+        s.n_inconsistent = (int64_t)h->h_counters[CNT_INCONSISTENT];
+        h->has_march = true;
+    } catch (const CudaFail &f) {
+        h->err = "am_march: " + f.msg;
+        return AM_ERR_CUDA;
+    }
+    return AM_OK;
+}
+
+int am_combine(am_handle *h, double scale, const double center[3])
+{
+    if (!h) return AM_ERR_ARG;
+    if (!h->has_march) {
+        h->err = "AnalyticMarching must be done first!";
+        return AM_ERR_STATE;
+    }
+    if (!center) {
+        h->err = "am_combine: null center";
+        return AM_ERR_ARG;
+    }
+    try {
+        cudaStream_t st = h->stream;
+        const long long nC = h->stats.n_corners;
+        const long long nS = h->n_states;
+        DevBuf owner, flag, vid, cvid, verts;
+        h->h_face_off.assign((size_t)nS + 1, 0);
+        if (nS) CK(cudaMemcpyAsync(h->h_face_off.data(), h->face_off.p, (size_t)(nS + 1) * 8, cudaMemcpyDeviceToHost, st));
+        h->h_vertices.clear();
+        h->h_corner_vid.assign((size_t)nC, 0);
+        unsigned long long *cnt = h->counters.as<unsigned long long>();
+        long long nV = 0;
+        if (nC > 0) {
+            owner.reserve((size_t)nC * 8); flag.reserve((size_t)nC * 4); vid.reserve((size_t)nC * 4);
+            cvid.reserve((size_t)nC * 4);
+            StitchArgs sa{};
+            sa.keys = h->keys.as<uint32_t>(); sa.hsum = h->hsum.as<unsigned long long>();
+            sa.face_off = h->face_off.as<long long>(); sa.face_edges = h->face_edges.as<int>();
+            sa.kw = h->kw; sa.kw4 = h->kw4; sa.L = h->L; sa.n_states = (int)nS;
+            sa.table = TableRef{h->table.as<unsigned long long>(), h->tcap - 1};
+            sa.owner = owner.as<long long>(); sa.counters = cnt;
+            const int G = h->G;
+            const unsigned gb = (unsigned)((nS * G + 255) / 256);
+            h->dispatch_group([&](auto g) { stitch_owner_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(sa); });
+            const unsigned cb = (unsigned)((nC + 255) / 256);
+            owner_flags_kernel<<<cb, 256, 0, st>>>(owner.as<long long>(), nC, flag.as<uint32_t>());
+            CK(cudaGetLastError());
+            h->scan(flag.as<uint32_t>(), vid.as<uint32_t>(), (int)nC, cnt + CNT_VERTS);
+            h->read_counters();
+            nV = (long long)h->h_counters[CNT_VERTS];
+            verts.reserve(std::max<size_t>((size_t)nV * 24, 24));
+            index_corners_kernel<<<cb, 256, 0, st>>>(owner.as<long long>(), vid.as<uint32_t>(), flag.as<uint32_t>(), nC,
+                                                    h->face_xyz.as<double>(), scale, center[0], center[1], center[2],
+                                                    cvid.as<int>(), verts.as<double>());
+            CK(cudaGetLastError());
+            h->h_vertices.resize((size_t)nV * 3);
+            CK(cudaMemcpyAsync(h->h_vertices.data(), verts.p, (size_t)nV * 24, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h->h_corner_vid.data(), cvid.p, (size_t)nC * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        h->read_counters();
+        h->stats.n_vertices = nV;
+        h->stats.n_stitch_miss = (int64_t)h->h_counters[CNT_STITCH_MISS];
+        owner.release(); flag.release(); vid.release(); cvid.release(); verts.release();
+        h->has_mesh = true;
+    } catch (const CudaFail &f) {
+        h->err = "am_combine: " + f.msg;
+        return AM_ERR_CUDA;
+    }
+    return AM_OK;
+}
+
+int am_export(am_handle *h, const char *path, int is_polymesh, int is_float32)
+{
+    if (!h) return AM_ERR_ARG;
+    if (!h->has_mesh) {
+        h->err = "CombineMesh must be done first!";
+        return AM_ERR_STATE;
+    }
+    if (!path) {
+        h->err = "am_export: null path";
+        return AM_ERR_ARG;
+    }
+    const long long nS = h->n_states;
+    const long long nV = h->stats.n_vertices;
+    long long nF = 0, nT = 0;
+    for (long long s = 0; s < nS; ++s) {
+        const long long k = h->h_face_off[s + 1] - h->h_face_off[s];
+        if (k >= 3) { ++nF; nT += k - 2; }
+    }
+    // header bytes exactly as reference backend/inc/polymesh.h:368-377
+    const char *ft = is_float32 ? "float" : "double";
+    std::string head = "ply\nformat binary_little_endian 1.0\nelement vertex " + std::to_string(nV) + "\nproperty " + ft +
+                       " x\nproperty " + ft + " y\nproperty " + ft + " z\nelement face " +
+                       std::to_string(is_polymesh ? nF : nT) + "\nproperty list uchar int vertex_index\nend_header\n";
+    const size_t vbytes = (size_t)nV * 3 * (is_float32 ? 4 : 8);
+    const size_t fbytes = is_polymesh ? (size_t)nF + (size_t)h->stats.n_corners * 4 : (size_t)nT * 13;
+    std::vector<unsigned char> buf(head.size() + vbytes + fbytes);
+    unsigned char *w = buf.data();
+    memcpy(w, head.data(), head.size());
+    w += head.size();
+    if (is_float32) {
+        float *o = reinterpret_cast<float *>(w);
+        for (size_t i = 0; i < (size_t)nV * 3; ++i) { const float f = (float)h->h_vertices[i]; memcpy(o + i, &f, 4); }
+    } else if (vbytes) {
+        memcpy(w, h->h_vertices.data(), vbytes);
+    }
+    w += vbytes;
+    for (long long s = 0; s < nS; ++s) {
+        const long long fo = h->h_face_off[s];
+        const int k = (int)(h->h_face_off[s + 1] - fo);
+        if (k < 3) continue;
+        const int *idx = h->h_corner_vid.data() + fo;
+        if (is_polymesh) {
+            *w++ = (unsigned char)k;
+            memcpy(w, idx, (size_t)k * 4);
+            w += (size_t)k * 4;
+        } else {
+            for (int j = 0; j + 2 < k; ++j) {   // fan (0, j+1, j+2), reference polymesh.h:405-416
+                *w++ = 3;
+                memcpy(w, idx, 4);
+                memcpy(w + 4, idx + j + 1, 4);
+                memcpy(w + 8, idx + j + 2, 4);
+                w += 12;
+            }
+        }
+    }
+    FILE *f = fopen(path, "wb");
+    if (!f) {
+        h->err = std::string("am_export: cannot open ") + path;
+        return AM_ERR_IO;
+    }
+    const size_t total = (size_t)(w - buf.data());
+    const size_t wr = fwrite(buf.data(), 1, total, f);
+    fclose(f);
+    if (wr != total) {
+        h->err = std::string("am_export: short write to ") + path;
+        return AM_ERR_IO;
+    }
+    return AM_OK;
+}
+
+int am_get_stats(const am_handle *h, am_stats *out)
+{
+    if (!h || !out) return AM_ERR_ARG;
+    *out = h->stats;
+    return AM_OK;
+}
+int am_key_words(const am_handle *h) { return h ? h->kw : 0; }
+int am_state_len(const am_handle *h) { return h ? h->L : 0; }
+
+int am_copy_states(const am_handle *h, uint32_t *keys, int64_t *face_off, int32_t *parent, int32_t *via_edge)
+{
+    if (!h || !h->has_march) return AM_ERR_STATE;
+    const size_t n = (size_t)h->n_states;
+    cudaError_t e = cudaSuccess;
+    if (keys && n) e = cudaMemcpy(keys, h->keys.p, n * h->kw * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && face_off) e = cudaMemcpy(face_off, h->face_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && parent && n) e = cudaMemcpy(parent, h->parent.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && via_edge && n) e = cudaMemcpy(via_edge, h->via.p, n * 4, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? AM_OK : AM_ERR_CUDA;
+}
+
+int am_copy_faces(const am_handle *h, int32_t *edge_ids, double *xyz)
+{
+    if (!h || !h->has_march) return AM_ERR_STATE;
+    const size_t n = (size_t)h->stats.n_corners;
+    cudaError_t e = cudaSuccess;
+    if (edge_ids && n) e = cudaMemcpy(edge_ids, h->face_edges.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && xyz && n) e = cudaMemcpy(xyz, h->face_xyz.p, n * 24, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? AM_OK : AM_ERR_CUDA;
+}
+
+int am_copy_mesh(const am_handle *h, double *vertices, int32_t *face_sizes, int32_t *face_index)
+{
+    if (!h || !h->has_mesh) return AM_ERR_STATE;
+    if (vertices && !h->h_vertices.empty()) memcpy(vertices, h->h_vertices.data(), h->h_vertices.size() * 8);
+    if (face_index && !h->h_corner_vid.empty()) memcpy(face_index, h->h_corner_vid.data(), h->h_corner_vid.size() * 4);
+    if (face_sizes) {
+        size_t f = 0;
+        for (long long s = 0; s < h->n_states; ++s) {
+            const long long k = h->h_face_off[s + 1] - h->h_face_off[s];
+            if (k >= 3) face_sizes[f++] = (int32_t)k;
+        }
+    }
+    return AM_OK;
+}
+
+int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, void *planes_out, void *equ_out)
+{
+    if (!h || !states || n < 1) return AM_ERR_ARG;
+    if (!h->weights_loaded) {
+        h->err = "am_debug_planes: load weights first";
+        return AM_ERR_STATE;
+    }
+    try {
+        cudaStream_t st = h->stream;
+        h->xstates.reserve((size_t)n * h->L, 0, false);
+        CK(cudaMemcpyAsync(h->xstates.p, states, (size_t)n * h->L,
+                           classify(states) == PK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        h->xkeys.reserve((size_t)n * h->kw * 4, 0, false);
+        const long long tot = n * h->kw;
+        pack_states_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->xstates.as<uint8_t>(), (int)n, h->L, h->kw,
+                                                                         h->xkeys.as<uint32_t>());
+        CK(cudaGetLastError());
+        h->ensure_chunk_scratch((size_t)n);
+        h->ev_used = 0;
+        h->spans.clear();
+        h->compose_chunk(h->xkeys.as<uint32_t>(), (int)n, iso);
+        CK(cudaStreamSynchronize(st));
+        std::vector<double> p1((size_t)h->n1 * 4), pl((size_t)n * h->R * 4), eq((size_t)n * 4);
+        CK(cudaMemcpy(p1.data(), h->P1.p, p1.size() * 8, cudaMemcpyDeviceToHost));
+        if (!pl.empty()) CK(cudaMemcpy(pl.data(), h->planes.p, pl.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(eq.data(), h->equ.p, eq.size() * 8, cudaMemcpyDeviceToHost));
+        for (int64_t s = 0; s < n; ++s)
+            for (int r = 0; r < h->L; ++r)
+                for (int c = 0; c < 4; ++c) {
+                    const double v = (r < h->n1) ? p1[4 * (size_t)r + c] : pl[((size_t)s * h->R + (r - h->n1)) * 4 + c];
+                    const size_t o = ((size_t)s * h->L + r) * 4 + c;
+                    if (h->f64) static_cast<double *>(planes_out)[o] = v;
+                    else static_cast<float *>(planes_out)[o] = (float)v;
+                }
+        for (size_t i = 0; i < eq.size(); ++i) {
+            if (h->f64) static_cast<double *>(equ_out)[i] = eq[i];
+            else static_cast<float *>(equ_out)[i] = (float)eq[i];
+        }
+        resolve_spans(h);
+    } catch (const CudaFail &f) {
+        h->err = "am_debug_planes: " + f.msg;
+        return AM_ERR_CUDA;
+    }
+    return AM_OK;
+}
+
+int am_compose_profile(const am_handle *h, double *ms_total, int64_t *launches, double *flops)
+{
+    if (!h) return AM_ERR_ARG;
+    if (ms_total) *ms_total = h->gemm_ms;
+    if (launches) *launches = h->gemm_launches;
+    if (flops) *flops = h->gemm_flops;
+    return AM_OK;
+}
+
+}  // extern "C"

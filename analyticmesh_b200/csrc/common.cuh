@@ -1,0 +1,49 @@
+// common.cuh -- shared definitions for the B200 Analytic Marching engine.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+namespace amb {
+
+constexpr int VSLOTS = 32;                  // working polygon capacity: one vertex per lane
+constexpr int VERT_MAX_REF = 20;            // reference inc/macro.h:42 (we keep larger polygons, but count them)
+constexpr double EPS_FEAS = 1e-20;          // reference inc/macro.h:18 (float64)
+constexpr uint64_t SLOT_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t CAND_TAG = 0x80000000u;  // low word of a slot: TAG | candidate index (this level), else state id
+constexpr int NO_SLOT = -1;
+
+// device-resident counters (index into an array of unsigned long long)
+enum Counter {
+    CNT_CORNERS = 0,      // running total of stored corners
+    CNT_FACES,
+    CNT_CANDIDATES,
+    CNT_UNBOUNDED,
+    CNT_OVERFLOW,
+    CNT_OVER_VERTMAX,
+    CNT_INCONSISTENT,
+    CNT_STITCH_MISS,
+    CNT_NEW,              // winners of the current level (scan total)
+    CNT_CHUNK_CORNERS,    // corners of the current chunk (scan total)
+    CNT_VERTS,            // unique vertices (combine)
+    CNT_NUM
+};
+
+__host__ __device__ inline uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// contribution of 32-bit word `v` at word index `w` to the additive key hash.
+// H(key) = sum_w word_mix(w, key[w])  (mod 2^64): flipping one bit updates H in O(1).
+__host__ __device__ inline uint64_t word_mix(uint32_t w, uint32_t v)
+{
+    return splitmix64((uint64_t(w + 1) << 32) | v);
+}
+
+__device__ __forceinline__ uint32_t slot_fp(uint64_t h) { return uint32_t(h >> 32); }
+
+}  // namespace amb

@@ -1,0 +1,126 @@
+/*
+ * am_b200.h -- C ABI of the B200-native Analytic Marching engine (libam_b200.so).
+ *
+ * This is the drop-in boundary for the reference's native extension `cuam`
+ * (reference backend/src/cuam.cpp:186-217: Init / AnalyticMarching / CombineMesh / ExportMesh /
+ * Destroy).  Plain pointers and sizes only -- no torch types.  The pybind11 module
+ * analyticmesh_b200/csrc/cuam_pybind.cpp keeps the reference's five names and keyword arguments
+ * and forwards to these entry points; INTEGRATION.md shows the binding a reference maintainer adds.
+ *
+ * Conventions
+ *   - every function returns AM_OK (0) or a negative error code; am_last_error() gives the text.
+ *     (The reference prints and exit()s the interpreter on CUDA errors, backend/inc/utilities.h:73-96.)
+ *   - data pointers may point to HOST or DEVICE memory; the library classifies them with
+ *     cudaPointerGetAttributes and stages host data itself.
+ *   - real type: double when the handle was created with is_f64 = 1, float otherwise.
+ *   - matrices are row-major (out, in), exactly as torch's nn.Linear.weight.
+ *   - bit j of a state <-> 32-bit word j/32, bit j%32 (reference backend/inc/states.h:63,76).
+ */
+#ifndef AM_B200_H
+#define AM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct am_handle am_handle;
+
+enum {
+    AM_OK = 0,
+    AM_ERR_ARG = -1,        /* malformed argument (shape, null pointer, float type) */
+    AM_ERR_STATE = -2,      /* call order violated (e.g. am_combine before am_march) */
+    AM_ERR_CUDA = -3,       /* a CUDA call failed */
+    AM_ERR_IO = -4,         /* file could not be written */
+    AM_ERR_CAPACITY = -5    /* an internal limit was hit (reported, never silent) */
+};
+
+/* counters of the last march; all monotone within one am_march call */
+typedef struct am_stats {
+    int64_t n_seeds;            /* seed states passed in */
+    int64_t n_unique_seeds;     /* after de-duplication */
+    int64_t n_states;           /* activation patterns visited (= processed) */
+    int64_t n_faces;            /* states whose polygon has >= 3 vertices */
+    int64_t n_corners;          /* sum of polygon sizes */
+    int64_t n_levels;           /* BFS levels */
+    int64_t n_candidates;       /* neighbour candidates generated (one per neuron edge) */
+    int64_t n_unbounded;        /* polygons still touching the artificial bounding box (dropped) */
+    int64_t n_overflow;         /* polygons that exceeded the 32-vertex working capacity (dropped) */
+    int64_t n_over_vertmax;     /* polygons with more than 20 vertices (kept; the reference truncates) */
+    int64_t n_inconsistent;     /* clip steps whose outside set was not one cyclic run */
+    int64_t n_vertices;         /* unique vertices after am_combine */
+    int64_t n_stitch_miss;      /* corners whose owner sibling lacked the matching corner */
+    int64_t max_level_states;   /* widest BFS level */
+    double  seconds_march;      /* device time of am_march (CUDA events) */
+    double  seconds_compose;    /* ... spent in the affine-composition kernels */
+    double  seconds_clip;       /* ... in the clipping kernel */
+    double  seconds_frontier;   /* ... in neighbour enumeration + visited-set kernels */
+    double  compose_flops;      /* algorithmic flops executed by the composition kernels */
+} am_stats;
+
+/* replaces cuam.Init (reference backend/src/cuam.cpp:58-95, src/cuam_kernel.cu:128-148).
+ * nodes: [3, n_1..n_D, 1]; arc_table: arc_rows = D rows of arc_cols ints, row = [k, src0, tm0, ...]. */
+int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const int *arc_table,
+              int arc_rows, int arc_cols, int num_extra_constraints);
+
+/* replaces cuam.AnalyticMarching (reference backend/src/cuam.cpp:97-184, src/cuam_kernel.cu:30-123).
+ * W, B: n_nodes-1 pointers; TM: n_tm pointers, tm_shapes: 2*n_tm ints ((0,0) = identity);
+ * states: n_seeds x L bytes (0/1, torch.bool layout); points: n_seeds x 3 reals;
+ * w_extra: n_extra x 3, b_extra: n_extra (inside is w.x + b < 0).  n_extra must equal the
+ * value given to am_create (the reference does not check this).
+ * stream: a cudaStream_t (NULL = default stream).  Returns after the march has completed. */
+int am_march(am_handle *h, const void *const *W, const void *const *B, const void *const *TM,
+             const int *tm_shapes, int n_tm, const uint8_t *states, const void *points, int64_t n_seeds,
+             const void *w_extra, const void *b_extra, int n_extra, double iso, int flip_insideout,
+             void *stream);
+
+/* replaces cuam.CombineMesh (reference src/cuam_kernel.cu:185-200): shared-vertex stitching +
+ * indexing; v_out = v * scale + center. */
+int am_combine(am_handle *h, double scale, const double center[3]);
+
+/* replaces cuam.ExportMesh (reference src/cuam_kernel.cu:205-246, inc/polymesh.h:350-423):
+ * binary little-endian PLY, polygons or fan triangles, float or double vertices. */
+int am_export(am_handle *h, const char *path, int is_polymesh, int is_float32);
+
+/* replaces cuam.Destroy (reference src/cuam_kernel.cu:153-179). NULL is allowed. */
+void am_destroy(am_handle *h);
+
+int am_get_stats(const am_handle *h, am_stats *out);
+const char *am_last_error(const am_handle *h);   /* h may be NULL: error of the last failed am_create */
+int am_key_words(const am_handle *h);            /* 32-bit words per stored key (multiple of 4) */
+int am_state_len(const am_handle *h);
+
+/* ---- parity accessors (new; the reference exposes only the PLY) ------------------------------ */
+
+/* per visited state, in state-id order (BFS order, deterministic):
+ *   keys      [n_states][am_key_words()]
+ *   face_off  [n_states + 1]  corner offsets (face i has face_off[i+1]-face_off[i] corners, 0 = no face)
+ *   parent    [n_states]      state id that discovered it (-1 for seeds)
+ *   via_edge  [n_states]      neuron whose bit was flipped (-1 for seeds)
+ * any pointer may be NULL. Host pointers only. */
+int am_copy_states(const am_handle *h, uint32_t *keys, int64_t *face_off, int32_t *parent, int32_t *via_edge);
+
+/* per corner: edge_ids[c] = constraint carrying the segment corner c -> next corner; xyz[c][3] in
+ * double regardless of the handle's real type (unscaled). Host pointers only. */
+int am_copy_faces(const am_handle *h, int32_t *edge_ids, double *xyz);
+
+/* after am_combine: vertices [n_vertices][3] (scaled, double), face_sizes [n_faces],
+ * face_index [n_corners of exported faces]. Host pointers only. */
+int am_copy_mesh(const am_handle *h, double *vertices, int32_t *face_sizes, int32_t *face_index);
+
+/* debug/parity: run only the affine-composition kernels for n given states and return the
+ * UNSIGNED rows planes[n][L][4] and the level planes equ[n][4] (host pointers, real type).
+ * Weights are the ones of the last am_march / am_load_weights call. */
+int am_load_weights(am_handle *h, const void *const *W, const void *const *B, const void *const *TM,
+                    const int *tm_shapes, int n_tm);
+int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, void *planes, void *equ);
+
+/* timing hook for bench.py: average device milliseconds of the dominant composition kernel over
+ * its launches in the last march, its launch count and the flops of those launches. */
+int am_compose_profile(const am_handle *h, double *ms_total, int64_t *launches, double *flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AM_B200_H */

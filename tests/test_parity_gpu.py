@@ -1,0 +1,148 @@
+"""Parity tests proper: the CUDA path (through the C ABI, host buffers) against the CPU oracle.
+
+Bar (BASELINE.json north_star): identical set of visited activation patterns and identical face
+adjacency (edge-id loops) bit for bit; vertex positions within 1e-5 relative (we assert 1e-9);
+|f(v)| no worse than the oracle's own residual.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden.cases import build_case
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["polytope", "chair_cube", "skipnet"]
+MEDIUM = ["chair", "mlp4x128s"]
+
+
+def _oracle(oracle_lib, case, **kw):
+    return oracle_lib.march(case["info"], case["states"], case["points"], case["w_extra"], case["b_extra"], **kw)
+
+
+@pytest.mark.parametrize("name", SMALL + MEDIUM)
+def test_region_set_and_loops_match_oracle(oracle_lib, name):
+    case = build_case(name)
+    eng = parity.run_engine(case)
+    orc = _oracle(oracle_lib, case)
+    rep = parity.compare_with_oracle(eng, orc, case["info"].state_len)
+    assert rep["keys_equal"], rep
+    assert rep["loops_equal"], rep
+    assert rep["max_vertex_err"] < 1e-9, rep          # north_star tolerance: 1e-5 relative
+    st = eng["stats"]
+    assert st["n_overflow"] == 0 and st["n_inconsistent"] == 0, st
+    assert st["n_faces"] == orc["n_faces"]
+
+
+@pytest.mark.parametrize("name", ["chair_cube", "skipnet", "mlp4x128s"])
+def test_planes_bit_exact_with_oracle(oracle_lib, name):
+    """The composition kernels use the oracle's summation order: planes must match bit for bit."""
+    from analyticmesh_b200 import cuam
+    case = build_case(name)
+    info = case["info"]
+    cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table, num_extra_constraints=0)
+    cuam.load_weights(info.weights, info.biases, info.arc_tm)
+    st = case["states"][:37]
+    planes, equ = cuam.debug_planes(st, iso=0.125)
+    for i in range(st.shape[0]):
+        p, e = oracle_lib.compose(info, st[i], iso=0.125)
+        assert np.array_equal(planes[i], p), (name, i, np.abs(planes[i] - p).max())
+        assert np.array_equal(equ[i], e), (name, i)
+
+
+@pytest.mark.parametrize("name", ["chair", "skipnet", "mlp4x128s"])
+def test_closed_surface_topology(name):
+    """Size-independent properties: every neuron edge is shared by exactly two faces, every vertex
+    by exactly four corners, Euler characteristic even."""
+    case = build_case(name)
+    eng = parity.run_engine(case)
+    L = case["info"].state_len
+    hist = parity.closed_manifold_report(eng, L)
+    assert set(hist) == {2}, hist
+    v, fs, fi = eng["mesh"]
+    st = eng["stats"]
+    assert st["n_stitch_miss"] == 0
+    assert fs.sum() == len(fi) == st["n_corners"]
+    val = np.bincount(fi, minlength=len(v))
+    assert val.min() == 4 and val.max() == 4, np.unique(val, return_counts=True)
+    n_edges = sum(hist.values())
+    assert (len(v) - n_edges + len(fs)) % 2 == 0
+    f_abs = np.abs(case["info"].forward(v)[0])
+    assert f_abs.max() < 1e-9, f_abs.max()
+
+
+def test_chair_known_answer():
+    """248 228 faces = 248 228 vertices, 496 456 edges, chi = 0."""
+    case = build_case("chair")
+    eng = parity.run_engine(case)
+    st = eng["stats"]
+    assert st["n_faces"] == 248228 and st["n_vertices"] == 248228 and st["n_corners"] == 992912, st
+    sizes = np.diff(eng["face_off"])
+    hist = dict(zip(*np.unique(sizes[sizes > 0], return_counts=True)))
+    assert hist == {3: 86083, 4: 97749, 5: 46744, 6: 14193, 7: 2963, 8: 427, 9: 59, 10: 9, 11: 1}
+
+
+def test_flip_insideout_reverses_loops():
+    case = build_case("chair_cube")
+    a = parity.engine_faces(parity.run_engine(case, flip=False, combine=False), case["info"].state_len)
+    b = parity.engine_faces(parity.run_engine(case, flip=True, combine=False), case["info"].state_len)
+    assert set(a) == set(b)
+    for k, va in a.items():
+        if va is None:
+            assert b[k] is None
+            continue
+        ga, gb = va[0], b[k][0]
+        assert sorted(ga) == sorted(gb)
+        # reversed cyclic order
+        n = len(ga)
+        r = list(reversed(ga))
+        i = r.index(gb[0])
+        assert tuple(r[i:] + r[:i]) == gb
+
+
+def test_deterministic_numbering():
+    case = build_case("skipnet")
+    a = parity.run_engine(case, combine=False)
+    b = parity.run_engine(case, combine=False)
+    assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["edges"], b["edges"])
+    assert np.array_equal(a["xyz"], b["xyz"]) and np.array_equal(a["parent"], b["parent"])
+
+
+def test_ply_export_bytes(tmp_path):
+    from analyticmesh_b200 import cuam
+    case = build_case("chair_cube")
+    eng = parity.run_engine(case)
+    v, fs, fi = eng["mesh"]
+    for poly in (True, False):
+        for f32 in (True, False):
+            p = str(tmp_path / f"m_{int(poly)}{int(f32)}.ply")
+            cuam.ExportMesh(file_path=p, is_polymesh=poly, is_float32=f32)
+            data = open(p, "rb").read()
+            ft = "float" if f32 else "double"
+            nf = len(fs) if poly else int((fs - 2).sum())
+            head = (f"ply\nformat binary_little_endian 1.0\nelement vertex {len(v)}\nproperty {ft} x\nproperty {ft} y\n"
+                    f"property {ft} z\nelement face {nf}\nproperty list uchar int vertex_index\nend_header\n").encode()
+            assert data.startswith(head)
+            body = data[len(head):]
+            vb = len(v) * 3 * (4 if f32 else 8)
+            got = np.frombuffer(body[:vb], dtype="<f4" if f32 else "<f8").reshape(-1, 3)
+            assert np.allclose(got, v.astype(np.float32) if f32 else v, rtol=0, atol=0)
+            assert len(body) - vb == (len(fs) + 4 * len(fi) if poly else 13 * nf)
+
+
+def test_errors_are_reported_not_fatal():
+    from analyticmesh_b200 import cuam
+    case = build_case("chair_cube")
+    info = case["info"]
+    cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table, num_extra_constraints=0)
+    with pytest.raises(RuntimeError):   # six extra constraints but the environment was created for zero
+        cuam.AnalyticMarching(weights=info.weights, biases=info.biases, states=case["states"], points=case["points"],
+                              arc_tm=[], w_extra_constraints=case["w_extra"], b_extra_constraints=case["b_extra"],
+                              iso=0.0, flip_insideout=False)
+    with pytest.raises(RuntimeError):   # wrong dtype
+        cuam.AnalyticMarching(weights=[w.astype(np.float32) for w in info.weights], biases=info.biases,
+                              states=case["states"], points=case["points"], arc_tm=[],
+                              w_extra_constraints=np.zeros((0, 3)), b_extra_constraints=np.zeros(0), iso=0.0,
+                              flip_insideout=False)
