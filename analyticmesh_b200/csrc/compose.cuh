@@ -13,7 +13,7 @@
 // states.  Register-tiled DFMA: on B200 the DFMA pipe and DMMA (mma.sync f64) both peak at
 // 37.0 TFLOP/s (tools/fp64_peak.cu, measured), and tcgen05 has no FP64 kind, so SIMT DFMA is the
 // roofline-equivalent choice -- and it keeps every output a single ascending-k FMA chain, i.e.
-// bit-identical to the CPU oracle (oracle/am_oracle.c masked_accumulate).
+// bit-identical to the CPU restatement used by the parity tests.
 //
 // Tile: 128 (m) x 32 states (= 128 columns) x 16 (k), 256 threads, 8x8 outputs per thread,
 // 3-stage cp.async pipeline, 97.5 KiB shared memory, one CTA per SM.

@@ -1,0 +1,234 @@
+"""CPU-only tests: ONNX codec, model container, initialiser, the oracle against known answers and the
+reference-generated golden vectors, and the C-ABI library's exported symbols (no compute without a GPU)."""
+import ctypes
+import hashlib
+import json
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from analyticmesh_b200 import MLP, load_model, save_model, zoo
+from analyticmesh_b200.initializers import dichotomy, states_of
+from analyticmesh_b200.netinfo import NetInfo
+from tests.golden.cases import build_case, CASES
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ---------------------------------------------------------------- ONNX codec / model -----------
+def test_load_chair_onnx():
+    m = load_model(os.path.join(GOLD, "chair.onnx"))
+    assert m.nodes == [3, 60, 60, 60, 60, 1] and m.arc_table == [[0]] * 4 and m.arc_tm_shape == []
+    assert load_model(open(os.path.join(GOLD, "chair.onnx"), "rb").read()).nodes == m.nodes
+    with pytest.raises(Exception):
+        load_model("/nonexistent.onnx")
+
+
+def test_onnx_roundtrip_all_skip_kinds(tmp_path):
+    """architecture of reference backend/test/test_onnx_io.py:148-154 (test_mlp_2)"""
+    torch.manual_seed(1)
+    m = MLP([3] + [80] * 5 + [1], [[1, 0, 0], [1, 1, 1], [0], [1, 3, 2], [1, 0, 3]],
+            [[80, 3], [0, 0], [80, 80], [1, 3]], enable_print=False)
+    p = str(tmp_path / "m.onnx")
+    save_model(m, p)
+    q = load_model(p)
+    assert q.nodes == m.nodes and q.arc_table == m.arc_table and q.arc_tm_shape == m.arc_tm_shape
+    x = torch.randn(17, 3)
+    assert torch.equal(m(x), q(x))
+
+
+def test_onnx_from_torch_exporter(tmp_path):
+    """custom nn.Module like reference backend/test/test_onnx_io.py:99-141 (identity + linear skips)"""
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l0, self.l1 = torch.nn.Linear(3, 20), torch.nn.Linear(20, 50)
+            self.l2, self.l3 = torch.nn.Linear(50, 20), torch.nn.Linear(20, 1)
+            self.sk = torch.nn.Linear(20, 20, bias=False)
+
+        def forward(self, x):
+            y1 = torch.relu(self.l0(x))
+            y2 = torch.relu(self.l1(y1))
+            y3 = torch.relu(self.l2(y2) + y1 + self.sk(y1))
+            return self.l3(y3)
+
+    torch.manual_seed(0)
+    net = Net()
+    p = str(tmp_path / "n.onnx")
+    save_model(net, p)
+    q = load_model(p)
+    assert q.nodes == [3, 20, 50, 20, 1]
+    assert q.arc_table == [[0], [2, 1, 0, 1, 1], [0]] and q.arc_tm_shape == [[0, 0], [20, 20]]
+    x = torch.randn(9, 3)
+    assert torch.allclose(net(x), q(x), atol=1e-6)
+
+
+def test_netinfo_forward_matches_torch():
+    c = build_case("skipnet")
+    x = np.random.RandomState(0).randn(50, 3) * 0.4
+    f, bits = c["info"].forward(x)
+    m = c["model"].double()
+    ft = m(torch.from_numpy(x)).reshape(-1).detach().numpy()
+    st = states_of(m, torch.from_numpy(x)).numpy()
+    c["model"].float()
+    assert np.allclose(f, ft, atol=1e-12) and np.array_equal(bits, st)
+
+
+def test_dichotomy_reproducible_and_on_surface():
+    m = zoo.sphere(width=64)
+    a = dichotomy(m, 0.0, 200, generator=torch.Generator().manual_seed(3), rng=random.Random(3))
+    b = dichotomy(m, 0.0, 200, generator=torch.Generator().manual_seed(3), rng=random.Random(3))
+    assert torch.equal(a, b) and a.shape == (200, 3)
+    assert float(m(a).abs().mean()) < 1e-3
+
+
+def test_seed_fixtures_are_current():
+    """the committed seeds are what make_seeds.py generates (guards against silent drift)"""
+    for name in ("polytope", "chair_cube"):
+        c = build_case(name)
+        f, bits = c["info"].forward(c["points"])
+        assert np.abs(f).mean() < 2e-3
+        assert c["states"].shape == (CASES[name][1], c["info"].state_len)
+
+
+# ---------------------------------------------------------------- oracle ----------------------
+def _canon(orc, res):
+    return orc.canonical_faces(res)
+
+
+def test_oracle_chair_known_answer(oracle_lib):
+    """SURVEY App. D (two independent float64 brute-force traversals): 248 228 faces, this histogram."""
+    c = build_case("chair")
+    r = oracle_lib.march(c["info"], c["states"], c["points"])
+    assert r["n_faces"] == 248228
+    cf = _canon(oracle_lib, r)
+    sizes = {}
+    for v in cf.values():
+        if v is not None:
+            sizes[len(v[0])] = sizes.get(len(v[0]), 0) + 1
+    assert sizes == {3: 86083, 4: 97749, 5: 46744, 6: 14193, 7: 2963, 8: 427, 9: 59, 10: 9, 11: 1}
+    keys = sorted(k for k, v in cf.items() if v is not None)
+    assert len(set(keys)) == 248228
+
+
+def test_oracle_self_consistency(oracle_lib):
+    """closed surface: every neuron edge shared by exactly two faces, |f(v)| tiny, centroid pattern = key"""
+    c = build_case("skipnet")
+    info = c["info"]
+    r = oracle_lib.march(info, c["states"], c["points"])
+    cf = _canon(oracle_lib, r)
+    L = info.state_len
+    inc = {}
+    verts, cents, keys = [], [], []
+    for k, v in cf.items():
+        if v is None:
+            continue
+        for e in v[0]:
+            kb = bytearray(k)
+            kb[e >> 3] &= ~(1 << (e & 7)) & 0xFF
+            inc[(bytes(kb), e)] = inc.get((bytes(kb), e), 0) + 1
+        verts.append(v[1])
+        cents.append(v[1].mean(0))
+        keys.append(k)
+    assert set(inc.values()) == {2}
+    assert np.abs(info.forward(np.concatenate(verts))[0]).max() < 1e-10
+    _, bits = info.forward(np.stack(cents))
+    got = [b.tobytes() for b in np.packbits(bits, axis=1, bitorder="little")]
+    assert got == keys
+
+
+def test_oracle_extra_constraints_and_seed_dedup(oracle_lib):
+    c = build_case("chair_cube")
+    r = oracle_lib.march(c["info"], c["states"], c["points"], c["w_extra"], c["b_extra"])
+    cf = _canon(oracle_lib, r)
+    L = c["info"].state_len
+    lo, hi = np.array(c["cube"][0]), np.array(c["cube"][1])
+    n_cut = 0
+    for v in cf.values():
+        if v is None:
+            continue
+        assert (v[1] >= lo - 1e-6).all() and (v[1] <= hi + 1e-6).all()
+        n_cut += any(e >= L for e in v[0])
+    assert n_cut > 10
+    twice = oracle_lib.march(c["info"], np.concatenate([c["states"]] * 2), np.concatenate([c["points"]] * 2),
+                             c["w_extra"], c["b_extra"])
+    assert twice["n_states"] == r["n_states"]
+
+
+def test_oracle_float32_variant_runs(oracle_lib):
+    c = build_case("chair_cube")
+    info32 = NetInfo.from_model(c["model"], dtype=np.float32)
+    r = oracle_lib.march(info32, c["states"], c["points"], c["w_extra"], c["b_extra"])
+    assert r["n_faces"] > 500
+
+
+GOLDEN_REF = sorted(f for f in os.listdir(GOLD) if f.startswith("ref_") and f.endswith(".json"))
+
+
+@pytest.mark.parametrize("fname", GOLDEN_REF or ["<none>"])
+def test_oracle_against_reference_golden(oracle_lib, fname):
+    """Pins the oracle to outputs of the reference's own CUDA build (tests/golden/make_golden_ref.py)."""
+    if fname == "<none>":
+        pytest.skip("no reference-generated golden vectors committed (see DESIGN.md: parity pinning)")
+    g = json.load(open(os.path.join(GOLD, fname)))
+    c = build_case(g["case"])
+    info = c["info"]
+    wsha = hashlib.sha256(b"".join(np.ascontiguousarray(w).tobytes() for w in info.weights)).hexdigest()
+    assert wsha == g["weights_sha256"], "weights differ between this machine and the golden run"
+    r = oracle_lib.march(info, c["states"], c["points"], c["w_extra"], c["b_extra"])
+    cf = {k: v for k, v in _canon(oracle_lib, r).items() if v is not None}
+    assert len(cf) == g["n_faces"] == g["n_unique_keys"]
+    digest = hashlib.sha256(b"".join(sorted(cf))).hexdigest()
+    assert digest == g["keys_sha256"]
+    for f in g["faces"]:
+        k = bytes.fromhex(f["key"])
+        ref_v = np.asarray(f["verts"])
+        ours = cf[k][1]
+        assert len(ours) == len(ref_v)
+        # same cyclic loop (any rotation), vertices within 1e-5 relative (north_star tolerance)
+        d = np.abs(ours[None, :, :] - ref_v[:, None, :]).max(-1)
+        start = int(np.argmin(d[0]))
+        rolled = np.roll(ours, -start, axis=0)
+        scale = max(1.0, float(np.abs(ref_v).max()))
+        assert np.abs(rolled - ref_v).max() / scale < 1e-5
+
+
+# ---------------------------------------------------------------- C ABI -----------------------
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "am_b200.h")).read()
+    declared = set(re.findall(r"\b(am_[a-z_]+)\s*\(", header))
+    assert {"am_create", "am_march", "am_combine", "am_export", "am_destroy"} <= declared
+    lib_path = os.path.join(ROOT, "analyticmesh_b200", "libam_b200.so")
+    assert os.path.exists(lib_path), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(lib_path)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    from analyticmesh_b200 import cuam
+    assert set(cuam.EXPORTS) == declared
+
+
+def test_cabi_rejects_malformed_architecture_without_gpu():
+    lib = ctypes.CDLL(os.path.join(ROOT, "analyticmesh_b200", "libam_b200.so"))
+    lib.am_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    nodes = (ctypes.c_int * 3)(2, 14, 1)          # input width must be 3
+    arc = (ctypes.c_int * 1)(0)
+    assert lib.am_create(ctypes.byref(h), 1, nodes, 3, arc, 1, 1, 0) == -1
+    assert b"malformed" in lib.am_last_error(None)
+    nodes = (ctypes.c_int * 3)(3, 14, 1)
+    assert lib.am_create(ctypes.byref(h), 1, nodes, 3, arc, 2, 1, 0) == -1     # wrong number of arc rows
+
+
+def test_product_path_does_not_touch_the_oracle():
+    """the product package must never import / call oracle/ (it is the checker, not a fallback)"""
+    pkg = os.path.join(ROOT, "analyticmesh_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "am_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
