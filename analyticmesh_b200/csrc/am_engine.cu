@@ -211,6 +211,7 @@ struct am_handle {
             TableRef t{table.as<unsigned long long>(), tcap - 1};
             rehash_kernel<<<(unsigned)((n_states + 255) / 256), 256, 0, stream>>>(hsum.as<unsigned long long>(),
                                                                                  (int)n_states, t);
+            ++stats.n_launches;
             CK(cudaGetLastError());
         }
     }
@@ -225,26 +226,33 @@ struct am_handle {
         const int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
         if (nb == 1) {
             scan_apply_kernel<<<1, SCAN_THREADS, 0, stream>>>(in, n, nullptr, out, total_dev);
+            ++stats.n_launches;
             CK(cudaGetLastError());
             return;
         }
         scan_a.reserve((size_t)nb * 4);
         scan_b.reserve((size_t)nb * 4 + (size_t)((nb + SCAN_TILE - 1) / SCAN_TILE) * 8 + 64);
         scan_reduce_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_a.as<uint32_t>());
+        ++stats.n_launches;
         CK(cudaGetLastError());
         if (nb <= SCAN_TILE) {
             scan_apply_kernel<<<1, SCAN_THREADS, 0, stream>>>(scan_a.as<uint32_t>(), nb, nullptr, scan_b.as<uint32_t>(),
                                                             nullptr);
+            ++stats.n_launches;
         } else {  // three levels: up to SCAN_TILE^3 items
             const int nb2 = (nb + SCAN_TILE - 1) / SCAN_TILE;
             uint32_t *l2 = scan_b.as<uint32_t>() + nb;
             scan_reduce_kernel<<<nb2, SCAN_THREADS, 0, stream>>>(scan_a.as<uint32_t>(), nb, l2);
+            ++stats.n_launches;
             scan_apply_kernel<<<1, SCAN_THREADS, 0, stream>>>(l2, nb2, nullptr, l2 + nb2, nullptr);
+            ++stats.n_launches;
             scan_apply_kernel<<<nb2, SCAN_THREADS, 0, stream>>>(scan_a.as<uint32_t>(), nb, l2 + nb2,
                                                               scan_b.as<uint32_t>(), nullptr);
+            ++stats.n_launches;
         }
         CK(cudaGetLastError());
         scan_apply_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_b.as<uint32_t>(), out, total_dev);
+        ++stats.n_launches;
         CK(cudaGetLastError());
     }
 
@@ -264,6 +272,7 @@ struct am_handle {
         size_t a = 0;
         if (t) a = span_begin();
         compose_gemm_kernel<<<grid, GM_THREADS, GM_SMEM_BYTES, stream>>>(g);
+        ++stats.n_launches;
         CK(cudaGetLastError());
         if (t) span_end(a, 0, flops);
         stats.compose_flops += flops;
@@ -284,6 +293,7 @@ struct am_handle {
                     const long long tot = (long long)Sc * M;
                     skip_input_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
                         out, 4LL * R, M, Sc, identity ? nullptr : TM[sk.tm].as<double>());
+                    ++stats.n_launches;
                 } else {
                     long long sstride;
                     const double *src = layer_rows(sk.src, &sstride);
@@ -291,6 +301,7 @@ struct am_handle {
                         const long long tot = (long long)Sc * M * 4;
                         skip_hidden_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
                             out, 4LL * R, src, sstride, keys0, kw, off[sk.src], M, Sc);
+                        ++stats.n_launches;
                     } else {
                         launch_gemm(TMt[sk.tm].as<double>(), tm_Mpad[sk.tm], M, n[sk.src], src, sstride, off[sk.src],
                                     out, nullptr, keys0, Sc, 1);
@@ -323,6 +334,7 @@ struct am_handle {
             }
         }
         equ_kernel<<<(Sc * 4 + 127) / 128, 128, 0, stream>>>(e);
+        ++stats.n_launches;
         CK(cudaGetLastError());
     }
 
@@ -495,8 +507,10 @@ void insert_seeds(am_handle *h, const uint8_t *states, const double *points, lon
     const long long tot = N * h->kw;
     pack_states_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->xstates.as<uint8_t>(), (int)N, h->L, h->kw,
                                                                      h->xkeys.as<uint32_t>());
+    ++h->stats.n_launches;
     hash_keys_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->xkeys.as<uint32_t>(), (int)N, h->kw,
                                                                  h->xh.as<unsigned long long>());
+    ++h->stats.n_launches;
     CK(cudaGetLastError());
     h->ensure_table((size_t)h->n_states + (size_t)N);
     h->ensure_states((size_t)h->n_states + (size_t)N);
@@ -513,10 +527,13 @@ void insert_seeds(am_handle *h, const uint8_t *states, const double *points, lon
     const int G = h->G;
     const unsigned gb = (unsigned)((N * G + 255) / 256);
     h->dispatch_group([&](auto g) { x_insert_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(x); });
+    ++h->stats.n_launches;
     x_count_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(x);
+    ++h->stats.n_launches;
     CK(cudaGetLastError());
     h->scan(h->nwin.as<uint32_t>(), h->wbase.as<uint32_t>(), (int)N, h->counters.as<unsigned long long>() + CNT_NEW);
     h->dispatch_group([&](auto g) { x_finalize_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(x); });
+    ++h->stats.n_launches;
     CK(cudaGetLastError());
     h->read_counters();
     h->n_states += (long long)h->h_counters[CNT_NEW];
@@ -554,6 +571,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         ca.out_cnt = h->f_cnt.as<int>(); ca.out_edges = h->f_edges.as<int>(); ca.out_verts = h->f_verts.as<double>();
         ca.counters = cnt;
         clip_kernel<<<(Sc + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, 0, st>>>(ca);
+        ++h->stats.n_launches;
         CK(cudaGetLastError());
         h->scan(h->f_cnt.as<uint32_t>(), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
         CompactArgs co{};
@@ -563,7 +581,9 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
         co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
         compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
+        ++h->stats.n_launches;
         bump_counters_kernel<<<1, 256, 0, st>>>(cnt, h->f_cnt.as<int>(), Sc);
+        ++h->stats.n_launches;
         CK(cudaGetLastError());
         if (timing) h->span_end(t0, 2);
         corners_upper += (long long)Sc * VSLOTS;
@@ -588,7 +608,9 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     const int G = h->G;
     const unsigned gb = (unsigned)((S * G + 255) / 256);
     h->dispatch_group([&](auto g) { expand_insert_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
+    ++h->stats.n_launches;
     count_winners_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a);
+    ++h->stats.n_launches;
     CK(cudaGetLastError());
     h->scan(h->nwin.as<uint32_t>(), h->wbase.as<uint32_t>(), (int)S, cnt + CNT_NEW);
     h->read_counters();                                   // the one host sync of the level
@@ -602,6 +624,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     a.n_states = (int)h->n_states;
     if (n_new > 0) {
         h->dispatch_group([&](auto g) { finalize_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
+        ++h->stats.n_launches;
         CK(cudaGetLastError());
     }
     if (timing) h->span_end(t0, 3);
@@ -833,8 +856,10 @@ int am_combine(am_handle *h, double scale, const double center[3])
             const int G = h->G;
             const unsigned gb = (unsigned)((nS * G + 255) / 256);
             h->dispatch_group([&](auto g) { stitch_owner_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(sa); });
+            ++h->stats.n_launches;
             const unsigned cb = (unsigned)((nC + 255) / 256);
             owner_flags_kernel<<<cb, 256, 0, st>>>(owner.as<long long>(), nC, flag.as<uint32_t>());
+            ++h->stats.n_launches;
             CK(cudaGetLastError());
             h->scan(flag.as<uint32_t>(), vid.as<uint32_t>(), (int)nC, cnt + CNT_VERTS);
             h->read_counters();
@@ -843,6 +868,7 @@ int am_combine(am_handle *h, double scale, const double center[3])
             index_corners_kernel<<<cb, 256, 0, st>>>(owner.as<long long>(), vid.as<uint32_t>(), flag.as<uint32_t>(), nC,
                                                     h->face_xyz.as<double>(), scale, center[0], center[1], center[2],
                                                     cvid.as<int>(), verts.as<double>());
+            ++h->stats.n_launches;
             CK(cudaGetLastError());
             h->h_vertices.resize((size_t)nV * 3);
             CK(cudaMemcpyAsync(h->h_vertices.data(), verts.p, (size_t)nV * 24, cudaMemcpyDeviceToHost, st));
@@ -993,6 +1019,7 @@ int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, 
         const long long tot = n * h->kw;
         pack_states_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->xstates.as<uint8_t>(), (int)n, h->L, h->kw,
                                                                          h->xkeys.as<uint32_t>());
+        ++h->stats.n_launches;
         CK(cudaGetLastError());
         h->ensure_chunk_scratch((size_t)n);
         h->ev_used = 0;
@@ -1021,6 +1048,49 @@ int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, 
         return AM_ERR_CUDA;
     }
     return AM_OK;
+}
+
+__global__ void fp64_probe_kernel(double *out, double a, double b, int iters)
+{
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+double am_fp64_peak_tflops(void)
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.0;
+    const int threads = 512, blocks = sms * 2, iters = 20000;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * threads * blocks) != cudaSuccess) return -1.0;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int r = 0; r < 4; ++r) {
+        cudaEventRecord(a);
+        fp64_probe_kernel<<<blocks, threads>>>(out, 1.000001, 1e-9, iters);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { best = -1.f; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    if (best <= 0.f) return -1.0;
+    return 2.0 * 8 * iters * (double)threads * blocks / (best * 1e-3) / 1e12;
 }
 
 int am_compose_profile(const am_handle *h, double *ms_total, int64_t *launches, double *flops)

@@ -29,14 +29,15 @@ _num_extra = 0
 class AmStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in (
         "n_seeds", "n_unique_seeds", "n_states", "n_faces", "n_corners", "n_levels", "n_candidates", "n_unbounded",
-        "n_overflow", "n_over_vertmax", "n_inconsistent", "n_vertices", "n_stitch_miss", "max_level_states")] + \
+        "n_overflow", "n_over_vertmax", "n_inconsistent", "n_vertices", "n_stitch_miss", "max_level_states",
+        "n_launches")] + \
         [(n, ctypes.c_double) for n in ("seconds_march", "seconds_compose", "seconds_clip", "seconds_frontier",
                                         "compose_flops")]
 
 
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",
            "am_key_words", "am_state_len", "am_copy_states", "am_copy_faces", "am_copy_mesh", "am_load_weights",
-           "am_debug_planes", "am_compose_profile")
+           "am_debug_planes", "am_compose_profile", "am_fp64_peak_tflops")
 
 
 def lib():
@@ -261,6 +262,12 @@ def mesh():
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     _err(lib().am_copy_mesh(_handle, p(v), p(fs), p(fi)), "mesh")
     return v, fs, fi
+
+
+def fp64_peak_tflops():
+    f = lib().am_fp64_peak_tflops
+    f.restype = ctypes.c_double
+    return float(f())
 
 
 def load_weights(weights, biases, arc_tm):

@@ -52,6 +52,7 @@ typedef struct am_stats {
     int64_t n_vertices;         /* unique vertices after am_combine */
     int64_t n_stitch_miss;      /* corners whose owner sibling lacked the matching corner */
     int64_t max_level_states;   /* widest BFS level */
+    int64_t n_launches;         /* kernels launched by am_march (+ am_combine once it has run) */
     double  seconds_march;      /* device time of am_march (CUDA events) */
     double  seconds_compose;    /* ... spent in the affine-composition kernels */
     double  seconds_clip;       /* ... in the clipping kernel */
@@ -119,6 +120,10 @@ int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, 
 /* timing hook for bench.py: average device milliseconds of the dominant composition kernel over
  * its launches in the last march, its launch count and the flops of those launches. */
 int am_compose_profile(const am_handle *h, double *ms_total, int64_t *launches, double *flops);
+
+/* roofline denominator measured on the spot: TFLOP/s of a register-resident DFMA loop that fills
+ * every SM of the current device (the same probe as tools/fp64_peak.cu). <= 0 on error. */
+double am_fp64_peak_tflops(void);
 
 #ifdef __cplusplus
 }

@@ -201,7 +201,7 @@ def test_oracle_against_reference_golden(oracle_lib, fname):
 # ---------------------------------------------------------------- C ABI -----------------------
 def test_cabi_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "am_b200.h")).read()
-    declared = set(re.findall(r"\b(am_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(am_[a-z0-9_]+)\s*\(", header))
     assert {"am_create", "am_march", "am_combine", "am_export", "am_destroy"} <= declared
     lib_path = os.path.join(ROOT, "analyticmesh_b200", "libam_b200.so")
     assert os.path.exists(lib_path), "run __graft_entry__.build() first"

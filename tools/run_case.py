@@ -35,5 +35,4 @@ for r in range(reps):
     s2 = cuam.stats()
     print(json.dumps(dict(case=name, wall_march=t1 - t0, wall_combine=t2 - t1, faces_per_s=s["n_faces"] / s["seconds_march"],
                           gemm_tflops=p["flops"] / max(p["ms_total"], 1e-9) / 1e9, gemm_ms=p["ms_total"],
-                          gemm_launches=p["launches"], n_vertices=s2["n_vertices"], stitch_miss=s2["n_stitch_miss"],
-                          **{k: v for k, v in s.items()})), flush=True)
+                          gemm_launches=p["launches"], **{**s, "n_vertices": s2["n_vertices"], "n_stitch_miss": s2["n_stitch_miss"]})), flush=True)
