@@ -114,6 +114,15 @@ struct am_handle {
     // ---- scratch ----
     DevBuf planes, equ, f_cnt, f_off, f_edges, f_verts, cand_slot, nwin, wbase, scan_a, scan_b, counters;
     DevBuf xkeys, xh, xpt, xslot, xstates;
+    // incremental composition: plane rows of the previous and the current level stay resident
+    DevBuf lvl_planes[2], bucket, perm, bcounts;
+    bool prev_resident = false;
+    long long prev_lb = 0, prev_S = 0;
+    int prev_buf = 0;
+    long long n_incremental_levels = 0;
+    bool incremental = true;
+    size_t resident_budget = 0;                 // bytes for the two resident level buffers
+    int *h_npre = nullptr;                      // pinned
     unsigned long long *h_counters = nullptr;   // pinned
     cudaStream_t stream = nullptr;
 
@@ -159,23 +168,26 @@ struct am_handle {
         for (auto &b : TMt) b.release();
         DevBuf *all[] = {&P1, &wout, &extra, &keys, &hsum, &parent, &via, &seedpt, &face_off, &face_edges, &face_xyz,
                          &table, &planes, &equ, &f_cnt, &f_off, &f_edges, &f_verts, &cand_slot, &nwin, &wbase, &scan_a,
-                         &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates};
+                         &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates, &lvl_planes[0], &lvl_planes[1],
+                         &bucket, &perm, &bcounts};
         for (DevBuf *b : all) b->release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear();
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr;
+        if (h_npre) cudaFreeHost(h_npre);
+        h_npre = nullptr;
     }
 
     // rows of hidden layer h for state 0 of a chunk + stride (doubles)
-    const double *layer_rows(int h, long long *stride) const
+    const double *layer_rows(const double *base, int h, long long *stride) const
     {
         if (h == 1) {
             *stride = 0;
             return P1.as<double>();
         }
         *stride = 4LL * R;
-        return planes.as<double>() + 4LL * (off[h] - n1);
+        return base + 4LL * (off[h] - n1);
     }
 
     void ensure_states(size_t want)
@@ -258,7 +270,7 @@ struct am_handle {
 
     // ---------------- composition of one chunk: keys of states [sid0, sid0+Sc) -------------------
     void launch_gemm(const double *Wt_, int Mpad_, int M, int K, const double *Bsrc, long long bstride, int bit0,
-                     double *out, const double *bias_, const uint32_t *keys0, int Sc, int accumulate)
+                     double *out, const double *bias_, const uint32_t *keys0, int Sc, int accumulate, const int *perm_)
     {
         GemmArgs g{};
         g.Wt = Wt_; g.Mpad = Mpad_; g.M = M; g.K = K;
@@ -266,45 +278,50 @@ struct am_handle {
         g.keys = keys0; g.kw = kw; g.bit0 = bit0;
         g.out = out; g.out_stride = 4LL * R;
         g.bias = bias_; g.S = Sc; g.accumulate = accumulate;
-        dim3 grid(Mpad_ / GM_BM, (Sc + GM_BS - 1) / GM_BS);
+        g.perm = perm_; g.m_tiles = Mpad_ / GM_BM;
+        dim3 grid((unsigned)(g.m_tiles * ((Sc + GM_BS - 1) / GM_BS)));
         const double flops = 2.0 * M * (double)K * 4.0 * Sc;
         const bool t = timing_on();
         size_t a = 0;
         if (t) a = span_begin();
-        compose_gemm_kernel<<<grid, GM_THREADS, GM_SMEM_BYTES, stream>>>(g);
+        compose_gemm_kernel<<<grid, GM_THREADS, gemm_smem_bytes(K), stream>>>(g);
         ++stats.n_launches;
         CK(cudaGetLastError());
         if (t) span_end(a, 0, flops);
         stats.compose_flops += flops;
     }
 
-    void compose_chunk(const uint32_t *keys0, int Sc, double iso)
+    // prm / npre: optional bucket-sorted permutation and, per fc layer h, the number of leading
+    // permutation slots whose states need layer h+1 recomputed (incremental mode); null = all states
+    void compose_chunk(const uint32_t *keys0, int S_all, double iso, double *base, const int *prm, const int *npre)
     {
         for (int h = 1; h < D; ++h) {   // fc layer h: hidden h -> hidden h+1
             long long bstride;
-            const double *Bsrc = layer_rows(h, &bstride);
-            double *out = planes.as<double>() + 4LL * (off[h + 1] - n1);
+            const double *Bsrc = layer_rows(base, h, &bstride);
+            double *out = base + 4LL * (off[h + 1] - n1);
+            const int Sc = npre ? npre[h] : S_all;
+            if (Sc == 0) continue;                 // nobody needs this layer recomputed
             launch_gemm(Wt[h].as<double>(), Mpad[h], n[h + 1], n[h], Bsrc, bstride, off[h], out, bias[h].as<double>(),
-                        keys0, Sc, 0);
+                        keys0, Sc, 0, prm);
             for (const Skip &sk : skips[h]) {
                 const bool identity = (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0);
                 const int M = n[h + 1];
                 if (sk.src == 0) {
                     const long long tot = (long long)Sc * M;
                     skip_input_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
-                        out, 4LL * R, M, Sc, identity ? nullptr : TM[sk.tm].as<double>());
+                        out, 4LL * R, M, Sc, identity ? nullptr : TM[sk.tm].as<double>(), prm, nullptr);
                     ++stats.n_launches;
                 } else {
                     long long sstride;
-                    const double *src = layer_rows(sk.src, &sstride);
+                    const double *src = layer_rows(base, sk.src, &sstride);
                     if (identity) {
                         const long long tot = (long long)Sc * M * 4;
                         skip_hidden_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
-                            out, 4LL * R, src, sstride, keys0, kw, off[sk.src], M, Sc);
+                            out, 4LL * R, src, sstride, keys0, kw, off[sk.src], M, Sc, prm, nullptr);
                         ++stats.n_launches;
                     } else {
                         launch_gemm(TMt[sk.tm].as<double>(), tm_Mpad[sk.tm], M, n[sk.src], src, sstride, off[sk.src],
-                                    out, nullptr, keys0, Sc, 1);
+                                    out, nullptr, keys0, Sc, 1, prm);
                     }
                 }
                 CK(cudaGetLastError());
@@ -314,7 +331,8 @@ struct am_handle {
         e.w = wout.as<double>();
         e.bias = bout;
         e.iso = iso;
-        e.in = layer_rows(D, &e.in_stride);
+        e.in = layer_rows(base, D, &e.in_stride);
+        const int Sc = S_all;
         e.keys = keys0; e.kw = kw; e.bit0 = off[D]; e.K = n[D]; e.S = Sc;
         e.equ = equ.as<double>();
         e.n_skips = 0;
@@ -328,7 +346,7 @@ struct am_handle {
                 q.kind = identity ? 1 : 2;
             } else {
                 q.kind = identity ? 3 : 4;
-                q.src = layer_rows(sk.src, &q.src_stride);
+                q.src = layer_rows(base, sk.src, &q.src_stride);
                 q.src_bit0 = off[sk.src];
                 q.src_n = n[sk.src];
             }
@@ -352,6 +370,10 @@ struct am_handle {
     void ensure_chunk_scratch(size_t Sc)
     {
         planes.reserve(std::max<size_t>((size_t)R * 32 * Sc, 64), 0, false);
+        ensure_chunk_scratch_no_planes(Sc);
+    }
+    void ensure_chunk_scratch_no_planes(size_t Sc)
+    {
         equ.reserve(Sc * 32, 0, false);
         f_cnt.reserve(Sc * 4, 0, false);
         f_off.reserve(Sc * 4, 0, false);
@@ -539,54 +561,123 @@ void insert_seeds(am_handle *h, const uint8_t *states, const double *points, lon
     h->n_states += (long long)h->h_counters[CNT_NEW];
 }
 
+// clip + scan + compact for the states [sid0, sid0+Sc) whose plane rows start at `planes_base`
+void clip_and_store(am_handle *h, long long sid0, int Sc, const double *planes_base, int flip)
+{
+    cudaStream_t st = h->stream;
+    unsigned long long *cnt = h->counters.as<unsigned long long>();
+    const uint32_t *keys0 = h->keys.as<uint32_t>() + (size_t)sid0 * h->kw;
+    ClipArgs ca{};
+    ca.keys = keys0; ca.kw = h->kw;
+    ca.P1 = h->P1.as<double>(); ca.n1 = h->n1;
+    ca.P = planes_base; ca.p_stride = 4LL * h->R;
+    ca.equ = h->equ.as<double>();
+    ca.extra = h->extra.as<double>();
+    ca.L = h->L; ca.E = h->E; ca.S = Sc; ca.flip = flip;
+    ca.seedpt = h->seedpt.as<double>() + (size_t)sid0 * 3;
+    ca.out_cnt = h->f_cnt.as<int>(); ca.out_edges = h->f_edges.as<int>(); ca.out_verts = h->f_verts.as<double>();
+    ca.counters = cnt;
+    clip_kernel<<<(Sc + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, 0, st>>>(ca);
+    ++h->stats.n_launches;
+    CK(cudaGetLastError());
+    h->scan(h->f_cnt.as<uint32_t>(), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
+    CompactArgs co{};
+    co.cnt = h->f_cnt.as<int>(); co.off = h->f_off.as<uint32_t>();
+    co.edges = h->f_edges.as<int>(); co.verts = h->f_verts.as<double>();
+    co.S = Sc; co.sid0 = (int)sid0;
+    co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
+    co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
+    compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
+    ++h->stats.n_launches;
+    bump_counters_kernel<<<1, 256, 0, st>>>(cnt, h->f_cnt.as<int>(), Sc);
+    ++h->stats.n_launches;
+    CK(cudaGetLastError());
+}
+
 void process_level(am_handle *h, long long lb, long long le, double iso, int flip)
 {
     cudaStream_t st = h->stream;
     const long long S = le - lb;
-    const size_t chunk = h->chunk_states();
     unsigned long long *cnt = h->counters.as<unsigned long long>();
     long long corners_upper = (long long)h->h_counters[CNT_CORNERS];
-    for (long long c0 = 0; c0 < S; c0 += (long long)chunk) {
-        const int Sc = (int)std::min<long long>((long long)chunk, S - c0);
-        const long long sid0 = lb + c0;
-        h->ensure_chunk_scratch((size_t)Sc);
-        h->ensure_corners((size_t)(corners_upper + (long long)Sc * VSLOTS), (size_t)corners_upper);
-        const uint32_t *keys0 = h->keys.as<uint32_t>() + (size_t)sid0 * h->kw;
+    const size_t per_state = std::max<size_t>((size_t)h->R * 32, 32);
 
-        size_t t0 = 0;
+    // Incremental mode: this level's plane rows stay resident (ping-pong with the previous level) so
+    // that children copy the rows of the layers before their flipped neuron instead of recomputing.
+    const bool resident = h->incremental && h->D >= 2 && S <= (1 << 26) &&
+                          2 * (size_t)S * per_state <= h->resident_budget;
+    if (resident) {
+        const int cur = h->prev_resident ? 1 - h->prev_buf : 0;
+        DevBuf &pb = h->lvl_planes[cur];
+        pb.reserve((size_t)S * per_state, 0, true);
+        double *base = pb.as<double>();
+        h->ensure_chunk_scratch_no_planes((size_t)S);
+        h->ensure_corners((size_t)(corners_upper + S * VSLOTS), (size_t)corners_upper);
+        const uint32_t *keys0 = h->keys.as<uint32_t>() + (size_t)lb * h->kw;
         const bool timing = h->timing_on();
+        size_t t0 = 0;
         if (timing) t0 = h->span_begin();
-        h->compose_chunk(keys0, Sc, iso);
-        if (timing) h->span_end(t0, 1);
 
+        // bucket the states by the layer of their flipped neuron, build the sorted permutation
+        const int D = h->D;
+        h->bucket.reserve((size_t)S * 4, 0, false);
+        h->perm.reserve((size_t)S * 4, 0, false);
+        h->bcounts.reserve((size_t)3 * (D + 2) * 4, 0, false);
+        int *counts = h->bcounts.as<int>(), *cursor = counts + (D + 2), *npre_d = counts + 2 * (D + 2);
+        CK(cudaMemsetAsync(counts, 0, (size_t)(D + 2) * 4, st));
+        LayerOffs lo{};
+        lo.D = D;
+        for (int l = 1; l <= D + 1; ++l) lo.off[l] = h->off[l];
+        const unsigned sb = (unsigned)((S + 255) / 256);
+        classify_kernel<<<sb, 256, 0, st>>>(h->via.as<int>(), h->parent.as<int>(), (int)lb, (int)S,
+                                            h->prev_resident ? (int)h->prev_lb : 0, h->prev_resident ? (int)h->prev_S : 0,
+                                            lo, h->bucket.as<int>(), counts);
+        ++h->stats.n_launches;
+        bucket_offsets_kernel<<<1, 32, 0, st>>>(counts, cursor, npre_d, D);
+        ++h->stats.n_launches;
+        scatter_kernel<<<sb, 256, 0, st>>>(h->bucket.as<int>(), (int)S, cursor, h->perm.as<int>());
+        ++h->stats.n_launches;
+        CK(cudaGetLastError());
+        std::vector<int> npre(D + 2, 0);
+        CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 1) * 4, cudaMemcpyDeviceToHost, st));
+        if (h->prev_resident) {
+            copy_parent_rows_kernel<<<(unsigned)((S + 7) / 8), 256, 0, st>>>(
+                h->bucket.as<int>(), h->parent.as<int>(), (int)lb, (int)S, (int)h->prev_lb,
+                h->lvl_planes[h->prev_buf].as<double>(), base, 4LL * h->R, lo, h->n1);
+            ++h->stats.n_launches;
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(st));
+        for (int b = 0; b <= D; ++b) npre[b] = h->h_npre[b];
+        h->compose_chunk(keys0, (int)S, iso, base, h->perm.as<int>(), npre.data());
+        if (timing) h->span_end(t0, 1);
         if (timing) t0 = h->span_begin();
-        ClipArgs ca{};
-        ca.keys = keys0; ca.kw = h->kw;
-        ca.P1 = h->P1.as<double>(); ca.n1 = h->n1;
-        ca.P = h->planes.as<double>(); ca.p_stride = 4LL * h->R;
-        ca.equ = h->equ.as<double>();
-        ca.extra = h->extra.as<double>();
-        ca.L = h->L; ca.E = h->E; ca.S = Sc; ca.flip = flip;
-        ca.seedpt = h->seedpt.as<double>() + (size_t)sid0 * 3;
-        ca.out_cnt = h->f_cnt.as<int>(); ca.out_edges = h->f_edges.as<int>(); ca.out_verts = h->f_verts.as<double>();
-        ca.counters = cnt;
-        clip_kernel<<<(Sc + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, 0, st>>>(ca);
-        ++h->stats.n_launches;
-        CK(cudaGetLastError());
-        h->scan(h->f_cnt.as<uint32_t>(), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
-        CompactArgs co{};
-        co.cnt = h->f_cnt.as<int>(); co.off = h->f_off.as<uint32_t>();
-        co.edges = h->f_edges.as<int>(); co.verts = h->f_verts.as<double>();
-        co.S = Sc; co.sid0 = (int)sid0;
-        co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
-        co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
-        compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
-        ++h->stats.n_launches;
-        bump_counters_kernel<<<1, 256, 0, st>>>(cnt, h->f_cnt.as<int>(), Sc);
-        ++h->stats.n_launches;
-        CK(cudaGetLastError());
+        clip_and_store(h, lb, (int)S, base, flip);
         if (timing) h->span_end(t0, 2);
-        corners_upper += (long long)Sc * VSLOTS;
+        h->prev_resident = true;
+        h->prev_buf = cur;
+        h->prev_lb = lb;
+        h->prev_S = S;
+        h->n_incremental_levels++;
+    } else {
+        h->prev_resident = false;
+        const size_t chunk = h->chunk_states();
+        for (long long c0 = 0; c0 < S; c0 += (long long)chunk) {
+            const int Sc = (int)std::min<long long>((long long)chunk, S - c0);
+            const long long sid0 = lb + c0;
+            h->ensure_chunk_scratch((size_t)Sc);
+            h->ensure_corners((size_t)(corners_upper + (long long)Sc * VSLOTS), (size_t)corners_upper);
+            const uint32_t *keys0 = h->keys.as<uint32_t>() + (size_t)sid0 * h->kw;
+            size_t t0 = 0;
+            const bool timing = h->timing_on();
+            if (timing) t0 = h->span_begin();
+            h->compose_chunk(keys0, Sc, iso, h->planes.as<double>(), nullptr, nullptr);
+            if (timing) h->span_end(t0, 1);
+            if (timing) t0 = h->span_begin();
+            clip_and_store(h, sid0, Sc, h->planes.as<double>(), flip);
+            if (timing) h->span_end(t0, 2);
+            corners_upper += (long long)Sc * VSLOTS;
+        }
     }
 
     // ---- neighbour enumeration + visited set ----------------------------------------------------
@@ -700,8 +791,17 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CK(cudaMallocHost(&h->h_counters, CNT_NUM * 8));
         memset(h->h_counters, 0, CNT_NUM * 8);
+        if (h->D + 2 > MAX_LAYERS) throw CudaFail{"more than 62 hidden layers"};
+        CK(cudaMallocHost(&h->h_npre, (size_t)(h->D + 2) * 4));
+        if (const char *e = getenv("AM_B200_INCREMENTAL")) h->incremental = atoi(e) != 0;
         h->counters.reserve(CNT_NUM * 8);
-        CK(cudaFuncSetAttribute(compose_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM_BYTES));
+        {
+            int kmax = 3;
+            for (int l = 1; l <= h->D; ++l) kmax = std::max(kmax, h->n[l]);
+            const size_t need = gemm_smem_bytes(kmax);
+            if (need > 227 * 1024) throw CudaFail{"hidden layers wider than ~31000 neurons are not supported"};
+            CK(cudaFuncSetAttribute(compose_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        }
     } catch (const CudaFail &f) {
         g_create_error = "am_create: " + f.msg;
         h->free_all();
@@ -782,6 +882,16 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         auto pts = fetch_real(points, (size_t)n_seeds * 3, h->f64);
         h->n_states = 0;
         h->level_begin.clear();
+        h->prev_resident = false;
+        h->n_incremental_levels = 0;
+        {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            double gib = 64.0;
+            if (const char *e = getenv("AM_B200_RESIDENT_GIB")) gib = atof(e);
+            const size_t have = free_b + h->lvl_planes[0].cap + h->lvl_planes[1].cap;
+            h->resident_budget = std::min<size_t>((size_t)(gib * (1ull << 30)), have / 2);
+        }
         CK(cudaMemsetAsync(h->counters.p, 0, CNT_NUM * 8, st));
         memset(h->h_counters, 0, CNT_NUM * 8);
         if (h->tcap) CK(cudaMemsetAsync(h->table.p, 0xFF, (size_t)h->tcap * 8, st));
@@ -1024,7 +1134,7 @@ int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, 
         h->ensure_chunk_scratch((size_t)n);
         h->ev_used = 0;
         h->spans.clear();
-        h->compose_chunk(h->xkeys.as<uint32_t>(), (int)n, iso);
+        h->compose_chunk(h->xkeys.as<uint32_t>(), (int)n, iso, h->planes.as<double>(), nullptr, nullptr);
         CK(cudaStreamSynchronize(st));
         std::vector<double> p1((size_t)h->n1 * 4), pl((size_t)n * h->R * 4), eq((size_t)n * 4);
         CK(cudaMemcpy(p1.data(), h->P1.p, p1.size() * 8, cudaMemcpyDeviceToHost));

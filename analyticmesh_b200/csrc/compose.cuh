@@ -15,8 +15,9 @@
 // roofline-equivalent choice -- and it keeps every output a single ascending-k FMA chain, i.e.
 // bit-identical to the CPU restatement used by the parity tests.
 //
-// Tile: 128 (m) x 32 states (= 128 columns) x 16 (k), 256 threads, 8x8 outputs per thread,
-// 3-stage cp.async pipeline, 97.5 KiB shared memory, one CTA per SM.
+// Tile: 128 (m) x 32 states (= 128 columns) x 16 (k), 512 threads (16 warps), 4x8 outputs per thread,
+// 3-stage cp.async pipeline, ~100 KiB shared memory, one CTA per SM.  The mask words of the tile's
+// states are staged in shared memory once, so the producer never waits on a dependent global load.
 #pragma once
 #include "common.cuh"
 
@@ -27,11 +28,13 @@ constexpr int GM_BS = 32;                 // states per tile
 constexpr int GM_BN = GM_BS * 4;          // 128 columns
 constexpr int GM_BK = 16;
 constexpr int GM_STAGES = 3;
-constexpr int GM_THREADS = 256;
+constexpr int GM_THREADS = 512;           // 16 warps: 4 per scheduler keep the DFMA pipe fed
 constexpr int GM_BS_STRIDE = GM_BN + 4;   // +32 B per k-row: conflict-free cp.async writes
 constexpr int GM_SMEM_A = GM_BK * GM_BM;                 // doubles per stage
 constexpr int GM_SMEM_B = GM_BK * GM_BS_STRIDE;
-constexpr size_t GM_SMEM_BYTES = size_t(GM_STAGES) * (GM_SMEM_A + GM_SMEM_B) * sizeof(double);
+constexpr size_t GM_SMEM_TILES = size_t(GM_STAGES) * (GM_SMEM_A + GM_SMEM_B) * sizeof(double);
+// + mask words of the 32 states of the tile: 32 x (K/32 + 2) uint32
+inline size_t gemm_smem_bytes(int K) { return GM_SMEM_TILES + size_t(GM_BS) * (K / 32 + 2) * sizeof(uint32_t); }
 
 struct GemmArgs {
     const double *Wt;           // [Kpad][Mpad], k-major, zero padded
@@ -44,8 +47,11 @@ struct GemmArgs {
     double *out;                // rows of the output layer for state 0: [M][4]
     long long out_stride;       // doubles between consecutive states
     const double *bias;         // [M] or nullptr
-    int S;                      // states in the chunk
+    int S;                      // states (permutation slots) of the launch
     int accumulate;             // out += result (hidden-layer skip with a transform)
+    const int *perm;            // optional: tile slot i works on state perm[i] (states sorted by the layer
+                                // of their flipped neuron, see classify_kernel); nullptr = identity
+    int m_tiles;                // Mpad / GM_BM; blockIdx.x = s_tile * m_tiles + m_tile
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
@@ -57,65 +63,79 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// 16 consecutive activation bits starting at bit position `pos` of a key
-__device__ __forceinline__ uint32_t key_bits16(const uint32_t *key, int kw, int pos)
-{
-    const int w = pos >> 5;
-    const uint32_t lo = key[w];
-    const uint32_t hi = (w + 1 < kw) ? key[w + 1] : 0u;
-    return __funnelshift_r(lo, hi, pos & 31) & 0xFFFFu;
-}
-
 __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmArgs a)
 {
     extern __shared__ __align__(16) double smem[];
     double *As = smem;                               // [STAGES][BK][BM]
     double *Bs = smem + GM_STAGES * GM_SMEM_A;       // [STAGES][BK][BS_STRIDE]
+    uint32_t *smask = reinterpret_cast<uint32_t *>(smem + GM_STAGES * (GM_SMEM_A + GM_SMEM_B));
 
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.x * GM_BM;
-    const int s0 = blockIdx.y * GM_BS;
+    const int m0 = (blockIdx.x % a.m_tiles) * GM_BM;      // m fastest: CTAs that share a B tile are co-resident
+    const int s0 = (blockIdx.x / a.m_tiles) * GM_BS;
+    const int S = a.S;
     const int KT = (a.K + GM_BK - 1) / GM_BK;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    // ---- mask words of the tile's 32 states -> shared memory (one coalesced pass) ---------------
+    // smask[sl][j] = key word (bit0/32 + j) of the state in tile slot sl; nw = words that cover the layer
+    const int w0 = a.bit0 >> 5, sh = a.bit0 & 31;
+    const int nw = (sh + a.K + 31) / 32 + 1;
+    for (int i = tid; i < GM_BS * nw; i += GM_THREADS) {
+        const int sl = i / nw, j = i - sl * nw;
+        const int slot = s0 + sl;
+        uint32_t v = 0;
+        if (slot < S && w0 + j < a.kw) {
+            const int st = a.perm ? a.perm[slot] : slot;
+            v = a.keys[(size_t)st * a.kw + w0 + j];
+        }
+        smask[i] = v;
+    }
 
     // ---- producer mapping ------------------------------------------------------------------
-    // A: 16 rows x 1 KiB = 1024 chunks of 16 B, 4 per thread, rows of 64 chunks (coalesced)
-    // B: per state 16 k x 32 B = 512 B contiguous in global; warp w stages states w, w+8, w+16, w+24
-    const int lane = tid & 31, warp = tid >> 5;
+    // A: 16 rows x 1 KiB = 1024 chunks of 16 B, 2 per thread (rows of 64 chunks, coalesced)
+    // B: per state 16 k x 32 B = 512 B contiguous in global; warp w stages tile slots w and w+16
     const int bk = lane >> 1, bhalf = lane & 1;      // k row and (xy | zc) half handled by this lane
+    long long bbase[2];                              // element offset of the state's rows, -1 = empty slot
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int slot = s0 + warp + 16 * i;
+        bbase[i] = (slot < S) ? (long long)(a.perm ? a.perm[slot] : slot) * a.b_stride : -1;
+    }
+    __syncthreads();                                 // smask visible
 
     auto load_stage = [&](int kt, int slot) {
         double *as = As + slot * GM_SMEM_A;
         double *bs = Bs + slot * GM_SMEM_B;
         const int k0 = kt * GM_BK;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
             const int c = tid + i * GM_THREADS;      // 0..1023
             const int row = c >> 6, col = (c & 63) * 2;
             cp_async16(as + row * GM_BM + col, a.Wt + (size_t)(k0 + row) * a.Mpad + m0 + col, 16);
         }
+        const int pos = sh + k0;                     // bit position of the slab inside the staged words
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int sl = warp + 8 * i;             // local state
-            const int s = s0 + sl;
+        for (int i = 0; i < 2; ++i) {
+            const int sl = warp + 16 * i;
             const int k = k0 + bk;
+            const uint32_t *mw = smask + sl * nw + (pos >> 5);
+            const uint32_t bits = __funnelshift_r(mw[0], mw[1], pos & 31);
             int bytes = 0;
             const double *src = a.Bsrc;
-            if (s < a.S && k < a.K) {
-                const uint32_t bits = key_bits16(a.keys + (size_t)s * a.kw, a.kw, a.bit0 + k0);
-                if ((bits >> bk) & 1u) {
-                    bytes = 16;
-                    src = a.Bsrc + (size_t)s * a.b_stride + (size_t)k * 4 + bhalf * 2;
-                }
+            if (bbase[i] >= 0 && k < a.K && ((bits >> bk) & 1u)) {
+                bytes = 16;
+                src = a.Bsrc + bbase[i] + (size_t)k * 4 + bhalf * 2;
             }
             cp_async16(bs + bk * GM_BS_STRIDE + sl * 4 + bhalf * 2, src, bytes);
         }
     };
 
-    // ---- consumer mapping ------------------------------------------------------------------
-    const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads
-    double acc[8][4][2];
+    // ---- consumer mapping: 16 (n) x 32 (m) threads, 4 rows x 8 columns each -----------------------
+    const int tx = tid & 15, ty = tid >> 4;
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -131,13 +151,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
         if (kt + GM_STAGES - 1 < KT) load_stage(kt + GM_STAGES - 1, (kt + GM_STAGES - 1) % GM_STAGES);
         cp_async_commit();
 
-        const double *as = As + (kt % GM_STAGES) * GM_SMEM_A + ty * 8;
+        const double *as = As + (kt % GM_STAGES) * GM_SMEM_A + ty * 4;
         const double *bs = Bs + (kt % GM_STAGES) * GM_SMEM_B + tx * 2;
 #pragma unroll
         for (int k = 0; k < GM_BK; ++k) {
-            double av[8], bv[4][2];
+            double av[4], bv[4][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
                 const double2 t = *reinterpret_cast<const double2 *>(as + k * GM_BM + 2 * i);
                 av[2 * i] = t.x;
                 av[2 * i + 1] = t.y;
@@ -149,7 +169,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
                 bv[j][1] = t.y;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     acc[i][j][0] = fma(av[i], bv[j][0], acc[i][j][0]);
@@ -163,12 +183,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
     const int comp0 = (tx & 1) * 2;                  // this thread holds components comp0, comp0+1
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int s = s0 + 8 * j + (tx >> 1);
-        if (s >= a.S) continue;
+        const int slot = s0 + 8 * j + (tx >> 1);
+        if (slot >= S) continue;
+        const int s = a.perm ? a.perm[slot] : slot;
         double *dst = a.out + (size_t)s * a.out_stride + comp0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m0 + ty * 8 + i;
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty * 4 + i;
             if (m >= a.M) continue;
             double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
             if (a.bias != nullptr && comp0 == 2) v.y += a.bias[m];
@@ -186,11 +207,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
 // ---- skip connections that are not GEMMs -----------------------------------------------------
 
 // from the raw input: P[s][m][0..2] += T[m][0..2]   (T == nullptr: += I3)   process.h:86-92,109-115
-__global__ void skip_input_kernel(double *out, long long out_stride, int M, int S, const double *T)
+__global__ void skip_input_kernel(double *out, long long out_stride, int M, int S, const double *T, const int *perm,
+                                  const int *n_active)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n_active) S = min(S, *n_active);
     if (t >= (long long)S * M) return;
-    const int s = int(t / M), m = int(t % M);
+    const int slot = int(t / M), m = int(t % M);
+    const int s = perm ? perm[slot] : slot;
     double *p = out + (size_t)s * out_stride + (size_t)m * 4;
     if (T != nullptr) {
         p[0] += T[3 * m + 0];
@@ -203,16 +227,85 @@ __global__ void skip_input_kernel(double *out, long long out_stride, int M, int 
 
 // identity skip from hidden layer `src`: out[s][m][:] += bit(s, src_bit0+m) * in[s][m][:]   process.h:93-105
 __global__ void skip_hidden_identity_kernel(double *out, long long out_stride, const double *in, long long in_stride,
-                                            const uint32_t *keys, int kw, int src_bit0, int M, int S)
+                                            const uint32_t *keys, int kw, int src_bit0, int M, int S, const int *perm,
+                                            const int *n_active)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n_active) S = min(S, *n_active);
     if (t >= (long long)S * M * 4) return;
     const int c = int(t & 3);
     const long long r = t >> 2;
-    const int s = int(r / M), m = int(r % M);
+    const int slot = int(r / M), m = int(r % M);
+    const int s = perm ? perm[slot] : slot;
     const int bit = src_bit0 + m;
     if ((keys[(size_t)s * kw + (bit >> 5)] >> (bit & 31)) & 1u)
         out[(size_t)s * out_stride + (size_t)m * 4 + c] += in[(size_t)s * in_stride + (size_t)m * 4 + c];
+}
+
+// ---- incremental composition ----------------------------------------------------------------------
+// A child differs from its parent in ONE bit, in hidden layer l_e.  The rows of hidden layers <= l_e
+// depend only on bits of layers < l_e, so they are bit-identical to the parent's rows: they are
+// copied from the previous level's plane buffer (kept resident) and only layers > l_e are recomputed.
+// States are bucketed by b = l_e (1 for seeds and for children whose parent rows are gone); the
+// launch of fc layer h works on the prefix of the bucket-sorted permutation with b <= h.
+constexpr int MAX_LAYERS = 64;
+struct LayerOffs {
+    int D;
+    int off[MAX_LAYERS + 2];      // off[h], h = 1..D+1
+};
+
+__global__ void classify_kernel(const int *via_edge, const int *parent, int lb, int S, int prev_lb, int prev_S,
+                                LayerOffs lo, int *bucket, int *counts /* [D+1], zeroed */)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int e = via_edge[lb + s], p = parent[lb + s];
+    int b = 1;
+    if (e >= 0 && p >= prev_lb && p < prev_lb + prev_S) {
+        while (b < lo.D && e >= lo.off[b + 1]) ++b;
+    }
+    bucket[s] = b;
+    atomicAdd(counts + b, 1);
+}
+
+// counts[b] -> cursor[b] = start of bucket b ; n_prefix[h] = #states with bucket <= h
+__global__ void bucket_offsets_kernel(int *counts, int *cursor, int *n_prefix, int D)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int run = 0;
+    for (int b = 0; b <= D; ++b) {
+        cursor[b] = run;
+        run += counts[b];
+        n_prefix[b] = run;
+        counts[b] = 0;
+    }
+}
+
+__global__ void scatter_kernel(const int *bucket, int S, int *cursor, int *perm)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    perm[atomicAdd(cursor + bucket[s], 1)] = s;
+}
+
+// rows of hidden layers 2..b of the parent -> own rows; one warp per state
+__global__ void copy_parent_rows_kernel(const int *bucket, const int *parent, int lb, int S, int prev_lb,
+                                        const double *prev, double *cur, long long stride, LayerOffs lo, int n1)
+{
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (s >= S) return;
+    const int b = bucket[s];
+    if (b < 2) return;
+    const long long n16 = (long long)(lo.off[b + 1] - n1) * 2;      // 16-byte pieces to copy
+    const uint4 *src = reinterpret_cast<const uint4 *>(prev + (size_t)(parent[lb + s] - prev_lb) * stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(cur + (size_t)s * stride);
+    long long i = lane;
+    for (; i + 96 < n16; i += 128) {                              // 4 independent 16 B loads in flight per lane
+        const uint4 v0 = src[i], v1 = src[i + 32], v2 = src[i + 64], v3 = src[i + 96];
+        dst[i] = v0; dst[i + 32] = v1; dst[i + 64] = v2; dst[i + 96] = v3;
+    }
+    for (; i < n16; i += 32) dst[i] = src[i];
 }
 
 // ---- output layer: the level plane (w_equ, b_equ - iso) ----------------------------------------
