@@ -10,14 +10,18 @@
 // as ONE FP64 GEMM  (M = n_out) x (N = 4*S) x (K = n_in)  whose B operand is masked by the packed
 // activation key while it is staged into shared memory (cp.async with src-size 0 zero-fills a
 // masked row, so inactive neurons cost no global read), and whose weights are shared by all S
-// states.  Register-tiled DFMA: on B200 the DFMA pipe and DMMA (mma.sync f64) both peak at
-// 37.0 TFLOP/s (tools/fp64_peak.cu, measured), and tcgen05 has no FP64 kind, so SIMT DFMA is the
-// roofline-equivalent choice -- and it keeps every output a single ascending-k FMA chain, i.e.
-// bit-identical to the CPU restatement used by the parity tests.
+// states.  The math is FP64 tensor-core DMMA (mma.sync.m8n8k4.f64): tcgen05 has no FP64 kind, and
+// on B200 DFMA and DMMA share the same 37.0 TFLOP/s peak (tools/fp64_peak.cu), but a register-tiled
+// DFMA kernel is capped near 64 % of it by register-file bandwidth (three 64-bit operands per FMA;
+// first version of this kernel, profiles/r01_compose_gemm_v1_ncu.md), while DMMA reads 4 operand
+// pairs per 256 FMAs.  DMMA was measured to be bit-identical to the ascending-k FMA chain
+// (tools/dmma_exact.cu: 128000/128000), so every output is still exactly the value the CPU
+// restatement used by the parity tests computes.
 //
-// Tile: 128 (m) x 32 states (= 128 columns) x 16 (k), 512 threads (16 warps), 4x8 outputs per thread,
-// 3-stage cp.async pipeline, ~100 KiB shared memory, one CTA per SM.  The mask words of the tile's
-// states are staged in shared memory once, so the producer never waits on a dependent global load.
+// Tile: 128 (m) x 32 states (= 128 columns) x 16 (k); 256 threads = 8 warps as 4 x 2, warp tile
+// 32 x 64 = 4 x 8 DMMA tiles; 4-stage cp.async pipeline, ~134 KiB shared memory, one CTA per SM.
+// The mask words of the tile's states are staged in shared memory once, so the producer never waits
+// on a dependent global load.
 #pragma once
 #include "common.cuh"
 
@@ -27,14 +31,15 @@ constexpr int GM_BM = 128;
 constexpr int GM_BS = 32;                 // states per tile
 constexpr int GM_BN = GM_BS * 4;          // 128 columns
 constexpr int GM_BK = 16;
-constexpr int GM_STAGES = 3;
-constexpr int GM_THREADS = 512;           // 16 warps: 4 per scheduler keep the DFMA pipe fed
-constexpr int GM_BS_STRIDE = GM_BN + 4;   // +32 B per k-row: conflict-free cp.async writes
-constexpr int GM_SMEM_A = GM_BK * GM_BM;                 // doubles per stage
+constexpr int GM_STAGES = 4;
+constexpr int GM_THREADS = 256;           // 8 warps as 4 (m) x 2 (n); warp tile 32 x 64 = 4 x 8 DMMA tiles
+constexpr int GM_AS_STRIDE = GM_BM + 4;   // +32 B per k-row: fragment loads and cp.async writes conflict-free
+constexpr int GM_BS_STRIDE = GM_BN + 4;
+constexpr int GM_SMEM_A = GM_BK * GM_AS_STRIDE;          // doubles per stage
 constexpr int GM_SMEM_B = GM_BK * GM_BS_STRIDE;
 constexpr size_t GM_SMEM_TILES = size_t(GM_STAGES) * (GM_SMEM_A + GM_SMEM_B) * sizeof(double);
-// + mask words of the 32 states of the tile: 32 x (K/32 + 2) uint32
-inline size_t gemm_smem_bytes(int K) { return GM_SMEM_TILES + size_t(GM_BS) * (K / 32 + 2) * sizeof(uint32_t); }
+// + mask words of the 32 states of the tile: 32 x nw uint32, nw = ceil((bit0 % 32 + K) / 32) + 1 <= K/32 + 4
+inline size_t gemm_smem_bytes(int K) { return GM_SMEM_TILES + size_t(GM_BS) * (K / 32 + 4) * sizeof(uint32_t); }
 
 struct GemmArgs {
     const double *Wt;           // [Kpad][Mpad], k-major, zero padded
@@ -63,10 +68,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// D(8x8) += A(8x4) * B(4x8), FP64.  Measured on B200 (tools/dmma_exact.cu): bit-identical to the
+// ascending-k chain c = fma(a_k, b_k, c), k = 0..3.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmArgs a)
 {
     extern __shared__ __align__(16) double smem[];
-    double *As = smem;                               // [STAGES][BK][BM]
+    double *As = smem;                               // [STAGES][BK][AS_STRIDE]
     double *Bs = smem + GM_STAGES * GM_SMEM_A;       // [STAGES][BK][BS_STRIDE]
     uint32_t *smask = reinterpret_cast<uint32_t *>(smem + GM_STAGES * (GM_SMEM_A + GM_SMEM_B));
 
@@ -93,13 +107,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
     }
 
     // ---- producer mapping ------------------------------------------------------------------
-    // A: 16 rows x 1 KiB = 1024 chunks of 16 B, 2 per thread (rows of 64 chunks, coalesced)
-    // B: per state 16 k x 32 B = 512 B contiguous in global; warp w stages tile slots w and w+16
+    // A: 16 rows x 1 KiB = 1024 chunks of 16 B, 4 per thread (rows of 64 chunks, coalesced)
+    // B: per state 16 k x 32 B = 512 B contiguous in global; warp w stages tile slots w, w+8, w+16, w+24
     const int bk = lane >> 1, bhalf = lane & 1;      // k row and (xy | zc) half handled by this lane
-    long long bbase[2];                              // element offset of the state's rows, -1 = empty slot
+    long long bbase[4];                              // element offset of the state's rows, -1 = empty slot
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int slot = s0 + warp + 16 * i;
+    for (int i = 0; i < 4; ++i) {
+        const int slot = s0 + warp + 8 * i;
         bbase[i] = (slot < S) ? (long long)(a.perm ? a.perm[slot] : slot) * a.b_stride : -1;
     }
     __syncthreads();                                 // smask visible
@@ -109,15 +123,15 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
         double *bs = Bs + slot * GM_SMEM_B;
         const int k0 = kt * GM_BK;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const int c = tid + i * GM_THREADS;      // 0..1023
             const int row = c >> 6, col = (c & 63) * 2;
-            cp_async16(as + row * GM_BM + col, a.Wt + (size_t)(k0 + row) * a.Mpad + m0 + col, 16);
+            cp_async16(as + row * GM_AS_STRIDE + col, a.Wt + (size_t)(k0 + row) * a.Mpad + m0 + col, 16);
         }
         const int pos = sh + k0;                     // bit position of the slab inside the staged words
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int sl = warp + 16 * i;
+        for (int i = 0; i < 4; ++i) {
+            const int sl = warp + 8 * i;
             const int k = k0 + bk;
             const uint32_t *mw = smask + sl * nw + (pos >> 5);
             const uint32_t bits = __funnelshift_r(mw[0], mw[1], pos & 31);
@@ -131,13 +145,16 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
         }
     };
 
-    // ---- consumer mapping: 16 (n) x 32 (m) threads, 4 rows x 8 columns each -----------------------
-    const int tx = tid & 15, ty = tid >> 4;
-    double acc[4][4][2];
+    // ---- consumer mapping: warp (wm, wn) owns rows [32 wm, +32) x columns [64 wn, +64) ------------
+    // DMMA fragments (PTX m8n8k4.f64): a = A[row = lane/4][k = lane%4], b = B[k = lane%4][col = lane/4],
+    //                                   c0,c1 = C[row = lane/4][col = 2 (lane%4) + {0,1}]
+    const int wm = warp & 3, wn = warp >> 2;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[4][8][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
     for (int st = 0; st < GM_STAGES - 1; ++st) {
@@ -151,45 +168,35 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
         if (kt + GM_STAGES - 1 < KT) load_stage(kt + GM_STAGES - 1, (kt + GM_STAGES - 1) % GM_STAGES);
         cp_async_commit();
 
-        const double *as = As + (kt % GM_STAGES) * GM_SMEM_A + ty * 4;
-        const double *bs = Bs + (kt % GM_STAGES) * GM_SMEM_B + tx * 2;
+        const double *as = As + (kt % GM_STAGES) * GM_SMEM_A + fk * GM_AS_STRIDE + wm * 32 + fr;
+        const double *bs = Bs + (kt % GM_STAGES) * GM_SMEM_B + fk * GM_BS_STRIDE + wn * 64 + fr;
 #pragma unroll
-        for (int k = 0; k < GM_BK; ++k) {
-            double av[4], bv[4][2];
+        for (int kk = 0; kk < GM_BK / 4; ++kk) {
+            double av[4], bv[8];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const double2 t = *reinterpret_cast<const double2 *>(as + k * GM_BM + 2 * i);
-                av[2 * i] = t.x;
-                av[2 * i + 1] = t.y;
-            }
+            for (int i = 0; i < 4; ++i) av[i] = as[kk * 4 * GM_AS_STRIDE + i * 8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double2 t = *reinterpret_cast<const double2 *>(bs + k * GM_BS_STRIDE + 32 * j);
-                bv[j][0] = t.x;
-                bv[j][1] = t.y;
-            }
+            for (int j = 0; j < 8; ++j) bv[j] = bs[kk * 4 * GM_BS_STRIDE + j * 8];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    acc[i][j][0] = fma(av[i], bv[j][0], acc[i][j][0]);
-                    acc[i][j][1] = fma(av[i], bv[j][1], acc[i][j][1]);
-                }
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
         }
     }
     cp_async_wait<0>();
 
     // ---- epilogue: + bias on column 3, store 16 B per (row, state) ---------------------------
-    const int comp0 = (tx & 1) * 2;                  // this thread holds components comp0, comp0+1
+    // columns 2 fk, 2 fk + 1 of an 8-column block = components comp0, comp0+1 of state (block*2 + fk/2)
+    const int comp0 = (fk & 1) * 2;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int slot = s0 + 8 * j + (tx >> 1);
+    for (int j = 0; j < 8; ++j) {
+        const int slot = s0 + wn * 16 + j * 2 + (fk >> 1);
         if (slot >= S) continue;
         const int s = a.perm ? a.perm[slot] : slot;
         double *dst = a.out + (size_t)s * a.out_stride + comp0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int m = m0 + ty * 4 + i;
+            const int m = m0 + wm * 32 + i * 8 + fr;
             if (m >= a.M) continue;
             double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
             if (a.bias != nullptr && comp0 == 2) v.y += a.bias[m];
