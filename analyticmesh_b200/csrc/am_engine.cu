@@ -122,6 +122,14 @@ struct am_handle {
     long long n_incremental_levels = 0;
     bool incremental = true;
     size_t resident_budget = 0;                 // bytes for the two resident level buffers
+    // sharded mode (one march over several GPUs): compose + clip of a state run on its owner rank only,
+    // the per-level polygons are combined with an all-reduce supplied by the host (NCCL through
+    // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
+    int shard_rank = 0, shard_world = 1;
+    am_allreduce_fn shard_cb = nullptr;
+    void *shard_user = nullptr;
+    DevBuf owner, xchg;
+    long long shard_owned_states = 0;
     int *h_npre = nullptr;                      // pinned
     unsigned long long *h_counters = nullptr;   // pinned
     cudaStream_t stream = nullptr;
@@ -169,7 +177,7 @@ struct am_handle {
         DevBuf *all[] = {&P1, &wout, &extra, &keys, &hsum, &parent, &via, &seedpt, &face_off, &face_edges, &face_xyz,
                          &table, &planes, &equ, &f_cnt, &f_off, &f_edges, &f_verts, &cand_slot, &nwin, &wbase, &scan_a,
                          &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates, &lvl_planes[0], &lvl_planes[1],
-                         &bucket, &perm, &bcounts};
+                         &bucket, &perm, &bcounts, &owner, &xchg};
         for (DevBuf *b : all) b->release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear();
@@ -201,6 +209,7 @@ struct am_handle {
         via.reserve(ncap * 4, keep * 4, false);
         seedpt.reserve(ncap * 24, keep * 24, false);
         face_off.reserve((ncap + 1) * 8, (keep + 1) * 8, false);
+        owner.reserve(ncap, keep, false);
         cap_states = ncap;
     }
     void ensure_corners(size_t want, size_t keep)
@@ -293,7 +302,9 @@ struct am_handle {
 
     // prm / npre: optional bucket-sorted permutation and, per fc layer h, the number of leading
     // permutation slots whose states need layer h+1 recomputed (incremental mode); null = all states
-    void compose_chunk(const uint32_t *keys0, int S_all, double iso, double *base, const int *prm, const int *npre)
+    // n_equ / equ_idx: states whose level plane is needed (all, or the owned ones in sharded mode)
+    void compose_chunk(const uint32_t *keys0, int S_all, double iso, double *base, const int *prm, const int *npre,
+                       int n_equ, const int *equ_idx)
     {
         for (int h = 1; h < D; ++h) {   // fc layer h: hidden h -> hidden h+1
             long long bstride;
@@ -332,7 +343,9 @@ struct am_handle {
         e.bias = bout;
         e.iso = iso;
         e.in = layer_rows(base, D, &e.in_stride);
-        const int Sc = S_all;
+        const int Sc = n_equ;
+        if (Sc <= 0) return;
+        e.idx = equ_idx;
         e.keys = keys0; e.kw = kw; e.bit0 = off[D]; e.K = n[D]; e.S = Sc;
         e.equ = equ.as<double>();
         e.n_skips = 0;
@@ -559,37 +572,65 @@ void insert_seeds(am_handle *h, const uint8_t *states, const double *points, lon
     CK(cudaGetLastError());
     h->read_counters();
     h->n_states += (long long)h->h_counters[CNT_NEW];
+    if (h->shard_world > 1 && h->n_states > 0) {
+        seed_owner_kernel<<<(unsigned)((h->n_states + 255) / 256), 256, 0, st>>>(h->owner.as<uint8_t>(), (int)h->n_states,
+                                                                                  h->shard_world);
+        ++h->stats.n_launches;
+        CK(cudaGetLastError());
+    }
 }
 
-// clip + scan + compact for the states [sid0, sid0+Sc) whose plane rows start at `planes_base`
-void clip_and_store(am_handle *h, long long sid0, int Sc, const double *planes_base, int flip)
+// per-level polygon scratch: separate buffers, or (sharded mode) three regions of one exchange buffer
+struct Scratch { int *cnt; int *edges; double *verts; };
+Scratch scratch_of(am_handle *h, size_t S)
 {
+    if (h->shard_world > 1) {
+        const size_t Sp = (S + 1) & ~size_t(1);
+        h->xchg.reserve(Sp * (4 + VSLOTS * 4 + VSLOTS * 24), 0, true);
+        char *b = h->xchg.as<char>();
+        return Scratch{reinterpret_cast<int *>(b), reinterpret_cast<int *>(b + Sp * 4),
+                       reinterpret_cast<double *>(b + Sp * 4 + Sp * VSLOTS * 4)};
+    }
+    return Scratch{h->f_cnt.as<int>(), h->f_edges.as<int>(), h->f_verts.as<double>()};
+}
+
+// clip the states idx[0..n) (or all Sc states when idx == nullptr) of the range starting at sid0
+void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, int flip, const int *idx, Scratch sc)
+{
+    if (n <= 0) return;
     cudaStream_t st = h->stream;
-    unsigned long long *cnt = h->counters.as<unsigned long long>();
-    const uint32_t *keys0 = h->keys.as<uint32_t>() + (size_t)sid0 * h->kw;
     ClipArgs ca{};
-    ca.keys = keys0; ca.kw = h->kw;
+    ca.keys = h->keys.as<uint32_t>() + (size_t)sid0 * h->kw; ca.kw = h->kw;
     ca.P1 = h->P1.as<double>(); ca.n1 = h->n1;
     ca.P = planes_base; ca.p_stride = 4LL * h->R;
     ca.equ = h->equ.as<double>();
     ca.extra = h->extra.as<double>();
-    ca.L = h->L; ca.E = h->E; ca.S = Sc; ca.flip = flip;
+    ca.L = h->L; ca.E = h->E; ca.S = n; ca.flip = flip;
     ca.seedpt = h->seedpt.as<double>() + (size_t)sid0 * 3;
-    ca.out_cnt = h->f_cnt.as<int>(); ca.out_edges = h->f_edges.as<int>(); ca.out_verts = h->f_verts.as<double>();
-    ca.counters = cnt;
-    clip_kernel<<<(Sc + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, 0, st>>>(ca);
+    ca.idx = idx;
+    ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
+    ca.counters = h->counters.as<unsigned long long>();
+    clip_kernel<<<(n + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, 0, st>>>(ca);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
-    h->scan(h->f_cnt.as<uint32_t>(), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
+}
+
+// scan + compact the polygons of the states [sid0, sid0+Sc) into the global CSR
+void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc)
+{
+    cudaStream_t st = h->stream;
+    unsigned long long *cnt = h->counters.as<unsigned long long>();
+    h->f_off.reserve((size_t)Sc * 4, 0, false);
+    h->scan(reinterpret_cast<uint32_t *>(sc.cnt), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
     CompactArgs co{};
-    co.cnt = h->f_cnt.as<int>(); co.off = h->f_off.as<uint32_t>();
-    co.edges = h->f_edges.as<int>(); co.verts = h->f_verts.as<double>();
+    co.cnt = sc.cnt; co.off = h->f_off.as<uint32_t>();
+    co.edges = sc.edges; co.verts = sc.verts;
     co.S = Sc; co.sid0 = (int)sid0;
     co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
     co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
     compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
     ++h->stats.n_launches;
-    bump_counters_kernel<<<1, 256, 0, st>>>(cnt, h->f_cnt.as<int>(), Sc);
+    bump_counters_kernel<<<1, 256, 0, st>>>(cnt, sc.cnt, Sc);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
 }
@@ -612,6 +653,8 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         pb.reserve((size_t)S * per_state, 0, true);
         double *base = pb.as<double>();
         h->ensure_chunk_scratch_no_planes((size_t)S);
+        const bool sharded = h->shard_world > 1;
+        Scratch sc = scratch_of(h, (size_t)S);
         h->ensure_corners((size_t)(corners_upper + S * VSLOTS), (size_t)corners_upper);
         const uint32_t *keys0 = h->keys.as<uint32_t>() + (size_t)lb * h->kw;
         const bool timing = h->timing_on();
@@ -622,24 +665,26 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         const int D = h->D;
         h->bucket.reserve((size_t)S * 4, 0, false);
         h->perm.reserve((size_t)S * 4, 0, false);
-        h->bcounts.reserve((size_t)3 * (D + 2) * 4, 0, false);
-        int *counts = h->bcounts.as<int>(), *cursor = counts + (D + 2), *npre_d = counts + 2 * (D + 2);
-        CK(cudaMemsetAsync(counts, 0, (size_t)(D + 2) * 4, st));
+        h->bcounts.reserve((size_t)3 * (D + 3) * 4, 0, false);
+        int *counts = h->bcounts.as<int>(), *cursor = counts + (D + 3), *npre_d = counts + 2 * (D + 3);
+        CK(cudaMemsetAsync(counts, 0, (size_t)(D + 3) * 4, st));
         LayerOffs lo{};
         lo.D = D;
         for (int l = 1; l <= D + 1; ++l) lo.off[l] = h->off[l];
         const unsigned sb = (unsigned)((S + 255) / 256);
         classify_kernel<<<sb, 256, 0, st>>>(h->via.as<int>(), h->parent.as<int>(), (int)lb, (int)S,
                                             h->prev_resident ? (int)h->prev_lb : 0, h->prev_resident ? (int)h->prev_S : 0,
-                                            lo, h->bucket.as<int>(), counts);
+                                            lo, h->bucket.as<int>(), counts, sharded ? h->owner.as<uint8_t>() : nullptr,
+                                            h->shard_rank);
         ++h->stats.n_launches;
         bucket_offsets_kernel<<<1, 32, 0, st>>>(counts, cursor, npre_d, D);
         ++h->stats.n_launches;
         scatter_kernel<<<sb, 256, 0, st>>>(h->bucket.as<int>(), (int)S, cursor, h->perm.as<int>());
         ++h->stats.n_launches;
         CK(cudaGetLastError());
-        std::vector<int> npre(D + 2, 0);
-        CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 1) * 4, cudaMemcpyDeviceToHost, st));
+        std::vector<int> npre(D + 3, 0);
+        CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 2) * 4, cudaMemcpyDeviceToHost, st));
+        if (sharded) CK(cudaMemsetAsync(h->xchg.p, 0, ((size_t)(S + 1) & ~size_t(1)) * (4 + VSLOTS * 4 + VSLOTS * 24), st));
         if (h->prev_resident) {
             copy_parent_rows_kernel<<<(unsigned)((S + 7) / 8), 256, 0, st>>>(
                 h->bucket.as<int>(), h->parent.as<int>(), (int)lb, (int)S, (int)h->prev_lb,
@@ -648,11 +693,21 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
             CK(cudaGetLastError());
         }
         CK(cudaStreamSynchronize(st));
-        for (int b = 0; b <= D; ++b) npre[b] = h->h_npre[b];
-        h->compose_chunk(keys0, (int)S, iso, base, h->perm.as<int>(), npre.data());
+        for (int b = 0; b <= D + 1; ++b) npre[b] = h->h_npre[b];
+        const int n_mine = npre[D];                       // states this rank composes and clips
+        h->shard_owned_states += n_mine;
+        h->compose_chunk(keys0, (int)S, iso, base, h->perm.as<int>(), npre.data(), sharded ? n_mine : (int)S,
+                         sharded ? h->perm.as<int>() : nullptr);
         if (timing) h->span_end(t0, 1);
         if (timing) t0 = h->span_begin();
-        clip_and_store(h, lb, (int)S, base, flip);
+        run_clip(h, lb, sharded ? n_mine : (int)S, base, flip, sharded ? h->perm.as<int>() : nullptr, sc);
+        if (sharded) {   // union of the ranks' polygons: every slot is non-zero on exactly one rank
+            CK(cudaStreamSynchronize(st));
+            const size_t Sp = ((size_t)S + 1) & ~size_t(1);
+            const long long n32 = (long long)(Sp * (4 + VSLOTS * 4 + VSLOTS * 24) / 4);
+            if (h->shard_cb(h->shard_user, h->xchg.p, n32) != 0) throw CudaFail{"the host all-reduce callback failed"};
+        }
+        store_faces(h, lb, (int)S, sc);
         if (timing) h->span_end(t0, 2);
         h->prev_resident = true;
         h->prev_buf = cur;
@@ -660,6 +715,8 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         h->prev_S = S;
         h->n_incremental_levels++;
     } else {
+        if (h->shard_world > 1)
+            throw CudaFail{"sharded mode needs the level's plane rows resident (raise AM_B200_RESIDENT_GIB)"};
         h->prev_resident = false;
         const size_t chunk = h->chunk_states();
         for (long long c0 = 0; c0 < S; c0 += (long long)chunk) {
@@ -671,10 +728,12 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
             size_t t0 = 0;
             const bool timing = h->timing_on();
             if (timing) t0 = h->span_begin();
-            h->compose_chunk(keys0, Sc, iso, h->planes.as<double>(), nullptr, nullptr);
+            h->compose_chunk(keys0, Sc, iso, h->planes.as<double>(), nullptr, nullptr, Sc, nullptr);
             if (timing) h->span_end(t0, 1);
             if (timing) t0 = h->span_begin();
-            clip_and_store(h, sid0, Sc, h->planes.as<double>(), flip);
+            Scratch sc = scratch_of(h, (size_t)Sc);
+            run_clip(h, sid0, Sc, h->planes.as<double>(), flip, nullptr, sc);
+            store_faces(h, sid0, Sc, sc);
             if (timing) h->span_end(t0, 2);
             corners_upper += (long long)Sc * VSLOTS;
         }
@@ -712,6 +771,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     a.face_off = h->face_off.as<long long>();
     a.keys_w = h->keys.as<uint32_t>(); a.hsum_w = h->hsum.as<unsigned long long>();
     a.parent = h->parent.as<int>(); a.via_edge = h->via.as<int>(); a.seedpt = h->seedpt.as<double>();
+    a.owner = h->shard_world > 1 ? h->owner.as<uint8_t>() : nullptr;
     a.n_states = (int)h->n_states;
     if (n_new > 0) {
         h->dispatch_group([&](auto g) { finalize_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
@@ -821,6 +881,20 @@ void am_destroy(am_handle *h)
     delete h;
 }
 
+int am_set_shard(am_handle *h, int rank, int world, am_allreduce_fn fn, void *user)
+{
+    if (!h) return AM_ERR_ARG;
+    if (world < 1 || world > 255 || rank < 0 || rank >= world || (world > 1 && !fn)) {
+        h->err = "am_set_shard: need 0 <= rank < world <= 255 and a callback when world > 1";
+        return AM_ERR_ARG;
+    }
+    h->shard_rank = rank;
+    h->shard_world = world;
+    h->shard_cb = fn;
+    h->shard_user = user;
+    return AM_OK;
+}
+
 int am_load_weights(am_handle *h, const void *const *W, const void *const *B, const void *const *TM, const int *tm_shapes,
                     int n_tm)
 {
@@ -884,6 +958,7 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         h->level_begin.clear();
         h->prev_resident = false;
         h->n_incremental_levels = 0;
+        h->shard_owned_states = 0;
         {
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
@@ -1134,7 +1209,7 @@ int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, 
         h->ensure_chunk_scratch((size_t)n);
         h->ev_used = 0;
         h->spans.clear();
-        h->compose_chunk(h->xkeys.as<uint32_t>(), (int)n, iso, h->planes.as<double>(), nullptr, nullptr);
+        h->compose_chunk(h->xkeys.as<uint32_t>(), (int)n, iso, h->planes.as<double>(), nullptr, nullptr, (int)n, nullptr);
         CK(cudaStreamSynchronize(st));
         std::vector<double> p1((size_t)h->n1 * 4), pl((size_t)n * h->R * 4), eq((size_t)n * 4);
         CK(cudaMemcpy(p1.data(), h->P1.p, p1.size() * 8, cudaMemcpyDeviceToHost));

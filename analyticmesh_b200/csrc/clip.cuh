@@ -39,6 +39,7 @@ struct ClipArgs {
     const double *extra;      // [E][4]
     int L, E, S, flip;
     const double *seedpt;     // [S][3] seed point of state 0 of the chunk
+    const int *idx;           // optional list of the states to process (sharded mode); S = its length
     int *out_cnt;             // [S]
     int *out_edges;           // [S][VSLOTS]
     double *out_verts;        // [S][VSLOTS][3]
@@ -72,8 +73,9 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32) clip_kernel(const ClipArgs a)
     __shared__ int s_ed[CLIP_WARPS][VSLOTS];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int s = blockIdx.x * CLIP_WARPS + wib;
-    if (s >= a.S) return;
+    const int slot = blockIdx.x * CLIP_WARPS + wib;
+    if (slot >= a.S) return;
+    const int s = a.idx ? a.idx[slot] : slot;
     double(*pl)[4] = s_pl[wib];
     double(*vx)[3] = s_vx[wib];
     int *ed = s_ed[wib];

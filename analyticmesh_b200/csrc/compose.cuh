@@ -261,26 +261,30 @@ struct LayerOffs {
     int off[MAX_LAYERS + 2];      // off[h], h = 1..D+1
 };
 
+// Sharded mode: a state owned by another rank goes to bucket D+1, which no launch touches.
 __global__ void classify_kernel(const int *via_edge, const int *parent, int lb, int S, int prev_lb, int prev_S,
-                                LayerOffs lo, int *bucket, int *counts /* [D+1], zeroed */)
+                                LayerOffs lo, int *bucket, int *counts /* [D+2], zeroed */, const uint8_t *owner,
+                                int rank)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int e = via_edge[lb + s], p = parent[lb + s];
     int b = 1;
-    if (e >= 0 && p >= prev_lb && p < prev_lb + prev_S) {
+    if (owner != nullptr && owner[lb + s] != rank) {
+        b = lo.D + 1;
+    } else if (e >= 0 && p >= prev_lb && p < prev_lb + prev_S) {
         while (b < lo.D && e >= lo.off[b + 1]) ++b;
     }
     bucket[s] = b;
     atomicAdd(counts + b, 1);
 }
 
-// counts[b] -> cursor[b] = start of bucket b ; n_prefix[h] = #states with bucket <= h
+// counts[b] -> cursor[b] = start of bucket b ; n_prefix[h] = #states with bucket <= h   (b = 0..D+1)
 __global__ void bucket_offsets_kernel(int *counts, int *cursor, int *n_prefix, int D)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int run = 0;
-    for (int b = 0; b <= D; ++b) {
+    for (int b = 0; b <= D + 1; ++b) {
         cursor[b] = run;
         run += counts[b];
         n_prefix[b] = run;
@@ -303,7 +307,7 @@ __global__ void copy_parent_rows_kernel(const int *bucket, const int *parent, in
     const int lane = threadIdx.x & 31;
     if (s >= S) return;
     const int b = bucket[s];
-    if (b < 2) return;
+    if (b < 2 || b > lo.D) return;
     const long long n16 = (long long)(lo.off[b + 1] - n1) * 2;      // 16-byte pieces to copy
     const uint4 *src = reinterpret_cast<const uint4 *>(prev + (size_t)(parent[lb + s] - prev_lb) * stride);
     uint4 *dst = reinterpret_cast<uint4 *>(cur + (size_t)s * stride);
@@ -333,6 +337,7 @@ struct EquArgs {
     const uint32_t *keys;
     int kw, bit0, K, S;
     double *equ;              // [S][4]
+    const int *idx;           // optional list of the states to compute (sharded mode); nullptr = all
     int n_skips;
     EquSkip skips[EQU_MAX_SKIPS];
 };
@@ -352,7 +357,7 @@ __global__ void equ_kernel(const EquArgs a)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.S * 4) return;
-    const int s = t >> 2, c = t & 3;
+    const int s = a.idx ? a.idx[t >> 2] : (t >> 2), c = t & 3;
     const uint32_t *key = a.keys + (size_t)s * a.kw;
     double v = masked_chain(a.w, a.in + (size_t)s * a.in_stride, key, a.bit0, a.K, c);
     if (c == 3) v += a.bias;

@@ -86,6 +86,7 @@ struct LevelArgs {
     unsigned long long *hsum_w;
     int *parent, *via_edge;
     double *seedpt;
+    uint8_t *owner;                       // sharded mode: rank that composes/clips the state (children inherit)
     int n_states;                         // states before this level's children are appended
 };
 
@@ -196,6 +197,7 @@ __global__ void finalize_kernel(const LevelArgs a)
             a.hsum_w[nid] = hash_flip(a.hsum[sid], a.keys + (size_t)sid * a.kw, e);
             a.parent[nid] = sid;
             a.via_edge[nid] = e;
+            if (a.owner) a.owner[nid] = a.owner[sid];
             const int j2 = (j + 1 == k) ? 0 : j + 1;
             const double *p = a.face_xyz + (size_t)(fo + j) * 3, *q2 = a.face_xyz + (size_t)(fo + j2) * 3;
             a.seedpt[(size_t)nid * 3 + 0] = 0.5 * (p[0] + q2[0]);
@@ -295,6 +297,12 @@ __global__ void x_finalize_kernel(const XArgs a)
         const int slot = a.x_slot[i];
         a.table.slots[slot] = (a.table.slots[slot] & 0xFFFFFFFF00000000ull) | uint32_t(nid);
     }
+}
+
+__global__ void seed_owner_kernel(uint8_t *owner, int n, int world)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) owner[i] = uint8_t(i % world);
 }
 
 // bool (N x L bytes) -> packed keys + additive hash; one thread per (seed, 32-bit word)

@@ -37,7 +37,7 @@ class AmStats(ctypes.Structure):
 
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",
            "am_key_words", "am_state_len", "am_copy_states", "am_copy_faces", "am_copy_mesh", "am_load_weights",
-           "am_debug_planes", "am_compose_profile", "am_fp64_peak_tflops")
+           "am_debug_planes", "am_compose_profile", "am_fp64_peak_tflops", "am_set_shard")
 
 
 def lib():
@@ -262,6 +262,31 @@ def mesh():
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     _err(lib().am_copy_mesh(_handle, p(v), p(fs), p(fi)), "mesh")
     return v, fs, fi
+
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+_shard_cb = None   # keeps the ctypes callback alive
+
+
+def set_shard(rank, world, allreduce):
+    """Spread ONE march over `world` processes (one GPU each).  `allreduce(device_ptr, n_int32)` must sum
+    the int32 buffer over all ranks in place and return after the result is visible on the device; see
+    analyticmesh_b200.parallel.make_allreduce for the torch.distributed implementation."""
+    global _shard_cb
+
+    def _cb(_user, ptr, n):
+        try:
+            allreduce(ptr, n)
+            return 0
+        except Exception as e:  # noqa: BLE001 - reported through the C ABI as a failed callback
+            print(f"(cuam) all-reduce callback failed: {e!r}")
+            return 1
+
+    _shard_cb = ALLREDUCE_FN(_cb) if world > 1 else None
+    fn = lib().am_set_shard
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    _err(fn(_handle, int(rank), int(world), ctypes.cast(_shard_cb, ctypes.c_void_p) if _shard_cb else None, None),
+         "set_shard")
 
 
 def fp64_peak_tflops():

@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the one exchange
+step of the sharded march (include/am_b200.h: am_set_shard).
+
+Per BFS level every rank clips the states it owns; the level's polygon scratch is zero in every slot
+a rank does not own, so an integer all-reduce(SUM) over the int32 view of the buffer is the exact
+union (each 32-bit word is non-zero on at most one rank).  Everything else (frontier, visited set,
+stitching) is replicated and deterministic, hence bit-identical on all ranks.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _DevMem:
+    """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, n_int32):
+        self.__cuda_array_interface__ = {"shape": (int(n_int32),), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def make_allreduce(group=None, device=None):
+    """Returns allreduce(ptr, n_int32) for cuam.set_shard.  `device` None/cuda: `ptr` is device memory
+    and NCCL is used; device == 'cpu': `ptr` is host memory (gloo) -- used by the CPU tests."""
+    is_cpu = device is not None and torch.device(device).type == "cpu"
+
+    def allreduce(ptr, n):
+        if is_cpu:
+            buf = (ctypes.c_int32 * n).from_address(ptr)
+            t = torch.from_numpy(np.frombuffer(buf, dtype=np.int32))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return
+        t = torch.as_tensor(_DevMem(ptr, n), device=device if device is not None else "cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.current_stream().synchronize()
+
+    return allreduce
+
+
+def owner_of_seeds(n_seeds_unique, world):
+    """Seed state i (after de-duplication, in id order) is owned by rank i % world; children inherit the
+    owner of the parent that discovered them (csrc/frontier.cuh finalize_kernel)."""
+    return np.arange(n_seeds_unique) % world

@@ -13,8 +13,9 @@ reference's `am_time` phase, backend/main.py:455-465).  Prints ONE JSON line on 
              process (am_fp64_peak_tflops; tools/fp64_peak.cu measured 37.0 TFLOP/s for DFMA and DMMA)
   cpu_baseline  the CPU oracle (oracle/am_oracle.c, OpenMP) on a bounded sample of the same workload
 
-N > 1: the path shards by shape (BASELINE config 5 style): every rank marches its own 8x512 network
-(seed = rank), no data-path collective; value = faces of all ranks / max-over-ranks time ("weak").
+N > 1: ONE march of the same network is spread over the N GPUs (am_set_shard): every rank composes and
+clips the states it owns, the per-level polygons are combined with one NCCL all-reduce, the frontier
+and visited set are replicated; value = faces of the mesh / max-over-ranks time ("strong").
 --impl reference: the reference algorithm's CPU restatement on the host cores (rank 0 only).
 """
 import argparse
@@ -137,7 +138,7 @@ def workload_name(args):
     d, w = args.workload[3:].rstrip("s").split("x")
     return (f"{args.workload}: SAL geometric-init ReLU MLP 3-[{w}]x{d}-1" +
             (" with a linear skip from the input into the middle layer" if args.workload.endswith("s") else "") +
-            f", r=0.5, torch.manual_seed(rank), {args.seeds} dichotomy seeds, iso 0, float64")
+            f", r=0.5, torch.manual_seed(0), {args.seeds} dichotomy seeds, iso 0, float64")
 
 
 def main():
@@ -166,7 +167,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from analyticmesh_b200 import cuam
-    info, points, states, init_point_time = build_workload(args.workload, rank, args.seeds)
+    info, points, states, init_point_time = build_workload(args.workload, 0, args.seeds)
     E0w, E0b = np.zeros((0, 3)), np.zeros(0)
     host = dict(weights=info.weights, biases=info.biases, states=states, points=points, arc_tm=info.arc_tm,
                 w_extra_constraints=E0w, b_extra_constraints=E0b)
@@ -180,6 +181,9 @@ def main():
     cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table, num_extra_constraints=0)
     torch.cuda.synchronize()
     init_cuda_time = time.time() - t0
+    if world > 1:
+        from analyticmesh_b200.parallel import make_allreduce
+        cuam.set_shard(rank, world, make_allreduce(device=dev))
 
     def barrier():
         if world > 1:
@@ -250,35 +254,36 @@ def main():
         t = torch.tensor([dt, e_dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, e_dt = float(t[0]), float(t[1])
-        c = torch.tensor([faces, e_faces, launches, h2d, d2h], dtype=torch.float64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        faces, e_faces, launches, h2d, d2h = (int(v) for v in c.tolist())
+        c = torch.tensor([launches, gemm_flops, gemm_ms, gemm_launches], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)   # the mesh is replicated: faces are counted once
+        launches, gemm_flops, gemm_ms, gemm_launches = int(c[0]), float(c[1]), float(c[2]) / world, int(c[3])
 
     if rank == 0:
         achieved = gemm_flops / max(gemm_ms * 1e-3, 1e-12) / 1e12
         fpf = flops_per_face(info.nodes)
         out = {
             "metric": METRIC, "value": faces / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "faces_per_step_rank0": last["n_faces"],
                        "states_per_step_rank0": last["n_states"], "bfs_levels": last["n_levels"],
                        "l2_note": "every step streams >= 9 GB of keys and >100 GB of plane rows through a 126 MB L2; "
                                   "inputs are far larger than L2, no flush needed",
-                       "parallelism": "1 process per GPU, sharded by shape (no data-path collective)" if world > 1
-                       else "single GPU",
+                       "parallelism": f"1 process per GPU; compose+clip sharded by state owner over {world} GPUs, one NCCL "
+                                      "all-reduce of the level's polygons per BFS level, frontier replicated"
+                       if world > 1 else "single GPU",
                        "mesh_time_s": {"init_point_time": init_point_time, "init_cuda_time": init_cuda_time,
                                        "am_time": dt / args.steps, "am_plus_combine_host_buffers": e_dt / args.steps,
                                        "export_time": export_time, "ply_bytes": ply_bytes},
                        "engine_stream_seconds_per_step": engine_s / args.steps,
                        "algorithmic_flops_per_face": fpf},
-            "e2e": {"value": e_faces / e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d // max(world, 1),
-                    "d2h_bytes_per_step": d2h // max(world, 1) if world > 1 else d2h},
+            "e2e": {"value": e_faces / e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "compose_gemm_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                         "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+                         "launches": gemm_launches, "avg_launch_ms": gemm_ms * world / max(gemm_launches, 1),
                          "peak_source": "DFMA loop measured in this process (am_fp64_peak_tflops); FP64 is not in "
                                         "MEASURED_PEAKS.json; tools/fp64_peak.cu: DFMA 37.0, DMMA 37.0, cuBLAS DGEMM 35.8"},
         }

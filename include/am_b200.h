@@ -87,6 +87,16 @@ int am_export(am_handle *h, const char *path, int is_polymesh, int is_float32);
 /* replaces cuam.Destroy (reference src/cuam_kernel.cu:153-179). NULL is allowed. */
 void am_destroy(am_handle *h);
 
+/* Sharded mode (new): ONE march spread over `world` GPUs, one process per GPU, every
+ * process calling am_march with identical arguments.  Compose + clip of a state run on its owner
+ * rank only (children inherit the owner of their parent, so the parent's plane rows are local);
+ * once per BFS level the library hands the level's polygon scratch (device pointer, n_int32 32-bit
+ * words, non-zero on exactly one rank per slot) to `fn`, which must sum it over all ranks in place
+ * (e.g. ncclAllReduce / torch.distributed.all_reduce on an int32 view) and return 0 after the result
+ * is visible on the device.  Frontier, visited set and mesh are replicated and bit-identical. */
+typedef int (*am_allreduce_fn)(void *user, void *device_ptr, int64_t n_int32);
+int am_set_shard(am_handle *h, int rank, int world, am_allreduce_fn fn, void *user);
+
 int am_get_stats(const am_handle *h, am_stats *out);
 const char *am_last_error(const am_handle *h);   /* h may be NULL: error of the last failed am_create */
 int am_key_words(const am_handle *h);            /* 32-bit words per stored key (multiple of 4) */

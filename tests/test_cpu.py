@@ -232,3 +232,42 @@ def test_product_path_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "am_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+# ---------------------------------------------------------------- multi-process host logic ------
+def _gloo_worker(rank, world, port, q):
+    import ctypes as ct
+    import torch.distributed as dist
+    from analyticmesh_b200.parallel import make_allreduce
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the level's polygon scratch: every slot is filled by exactly one rank (owner = slot % world)
+    n = 4096
+    buf = np.zeros(n, dtype=np.int32)
+    mine = np.arange(n) % world == rank
+    buf[mine] = (np.arange(n, dtype=np.int64)[mine] * 2654435761 % 2**31).astype(np.int32)
+    make_allreduce(device="cpu")(buf.ctypes.data, n)
+    expect = (np.arange(n, dtype=np.int64) * 2654435761 % 2**31).astype(np.int32)
+    q.put((rank, bool(np.array_equal(buf, expect))))
+    dist.destroy_process_group()
+
+
+def test_allreduce_union_world2_gloo():
+    """N>1 host path (analyticmesh_b200/parallel.py) with world_size 2 on CPU: the integer all-reduce of
+    disjointly filled buffers is the exact union on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_seed_owner_rule():
+    from analyticmesh_b200.parallel import owner_of_seeds
+    assert owner_of_seeds(5, 2).tolist() == [0, 1, 0, 1, 0]
