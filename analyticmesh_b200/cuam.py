@@ -37,7 +37,8 @@ class AmStats(ctypes.Structure):
 
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",
            "am_key_words", "am_state_len", "am_copy_states", "am_copy_faces", "am_copy_mesh", "am_load_weights",
-           "am_debug_planes", "am_compose_profile", "am_fp64_peak_tflops", "am_set_shard")
+           "am_debug_planes", "am_compose_profile", "am_fp64_peak_tflops", "am_set_shard", "am_ply_parse_faces",
+           "am_ply_pack_faces")
 
 
 def lib():

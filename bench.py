@@ -254,9 +254,12 @@ def main():
         t = torch.tensor([dt, e_dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, e_dt = float(t[0]), float(t[1])
-        c = torch.tensor([launches, gemm_flops, gemm_ms, gemm_launches], dtype=torch.float64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)   # the mesh is replicated: faces are counted once
-        launches, gemm_flops, gemm_ms, gemm_launches = int(c[0]), float(c[1]), float(c[2]) / world, int(c[3])
+        # the mesh is replicated: faces are counted once; the roofline is per GPU (mean over ranks)
+        c = torch.tensor([launches, gemm_flops / max(gemm_ms, 1e-9), gemm_ms, gemm_launches], dtype=torch.float64,
+                         device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        launches, gemm_ms, gemm_launches = int(c[0]), float(c[2]) / world, int(c[3]) // world
+        gemm_flops = float(c[1]) / world * gemm_ms          # so that achieved = mean over ranks of flops/ms
 
     if rank == 0:
         achieved = gemm_flops / max(gemm_ms * 1e-3, 1e-12) / 1e12
@@ -283,7 +286,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "compose_gemm_kernel", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                         "launches": gemm_launches, "avg_launch_ms": gemm_ms * world / max(gemm_launches, 1),
+                         "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                          "peak_source": "DFMA loop measured in this process (am_fp64_peak_tflops); FP64 is not in "
                                         "MEASURED_PEAKS.json; tools/fp64_peak.cu: DFMA 37.0, DMMA 37.0, cuBLAS DGEMM 35.8"},
         }

@@ -135,6 +135,17 @@ int am_compose_profile(const am_handle *h, double *ms_total, int64_t *launches, 
  * every SM of the current device (the same probe as tools/fp64_peak.cu). <= 0 on error. */
 double am_fp64_peak_tflops(void);
 
+/* ---- polygon-mesh file helpers (host only; native part of analyticmesh_b200.polymesh.PolyMesh, the
+ * counterpart of reference backend/libpolytools/src/polylib.cpp:134-268, 349-393) ------------------ */
+
+/* face records of a binary PLY body: [uchar k][k x int32][3 x uchar colour if has_colors].
+ * indices == NULL: sizing pass (counts, *n_indices only).  Returns bytes consumed or -1. */
+int64_t am_ply_parse_faces(const uint8_t *body, int64_t nbytes, int64_t n_faces, int has_colors, int32_t *counts,
+                           int32_t *indices, int64_t cap, uint8_t *colors, int64_t *n_indices);
+/* inverse; out == NULL: returns the size only */
+int64_t am_ply_pack_faces(const int32_t *counts, const int32_t *indices, int64_t n_faces, const uint8_t *colors,
+                          uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

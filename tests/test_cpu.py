@@ -271,3 +271,30 @@ def test_allreduce_union_world2_gloo():
 def test_seed_owner_rule():
     from analyticmesh_b200.parallel import owner_of_seeds
     assert owner_of_seeds(5, 2).tolist() == [0, 1, 0, 1, 0]
+
+
+# ---------------------------------------------------------------- polygon-mesh files ------------
+def test_polymesh_roundtrip_and_poly2tri(tmp_path):
+    """behaviour of reference backend/libpolytools (polylib.cpp:134-268, 349-393, 503-569)"""
+    from analyticmesh_b200.polymesh import PolyMesh, get_faces_num, load_ply_header, poly2tri
+    verts = [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 0.5, 1]]
+    faces = [[0, 1, 2, 3], [0, 1, 4], [1, 2, 4, 4]]
+    m = PolyMesh(vertices=verts, faces=faces, colors=[[255, 0, 0], [0, 255, 0], [0, 0, 255]])
+    ply, off, tri = str(tmp_path / "a.ply"), str(tmp_path / "a.off"), str(tmp_path / "t.ply")
+    m.save(ply)
+    n = PolyMesh(ply)
+    assert n.faces() == faces and n.colors() == [[255, 0, 0], [0, 255, 0], [0, 0, 255]]
+    assert np.allclose(n.vertices(), verts)
+    assert n.is_polymesh() and n.num_polyfaces() == 3 and n.num_trifaces() == 5
+    assert load_ply_header(ply) == {'storing_type': 'binary_little_endian', 'storing_version': 1.0, 'vertex_num': 5,
+                                    'face_num': 3}
+    assert get_faces_num(ply) == {'poly': 3, 'tri': 5}
+    poly2tri(ply, tri)
+    t = PolyMesh(tri)
+    assert t.faces() == [[0, 1, 2], [0, 2, 3], [0, 1, 4], [1, 2, 4]]       # degenerate (1,4,4) dropped
+    assert t.colors() == [[255, 0, 0], [255, 0, 0], [0, 255, 0], [0, 0, 255]] and not t.is_polymesh()
+    m.save(off)
+    o = PolyMesh(off)
+    assert o.faces() == faces and np.allclose(o.vertices(), verts)
+    with pytest.raises(RuntimeError):
+        PolyMesh(str(tmp_path / "x.stl"))
