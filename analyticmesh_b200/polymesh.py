@@ -190,7 +190,7 @@ class PolyMesh:
             for i in range(len(self._cnt)):
                 row = [str(self._cnt[i])] + [str(v) for v in self._idx[off[i]:off[i + 1]]]
                 if len(self._col):
-                    row += [str(int(c)) for c in self._col[i]]
+                    row += [f"{int(c) / 255:g}" for c in self._col[i]]   # OFF colours are floats in [0, 1]
                 f.write(" ".join(row) + "\n")
 
 
