@@ -125,6 +125,7 @@ struct am_handle {
     // sharded mode (one march over several GPUs): compose + clip of a state run on its owner rank only,
     // the per-level polygons are combined with an all-reduce supplied by the host (NCCL through
     // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
+    int gemm_variant = 0;
     int shard_rank = 0, shard_world = 1;
     am_allreduce_fn shard_cb = nullptr;
     void *shard_user = nullptr;
@@ -288,12 +289,24 @@ struct am_handle {
         g.out = out; g.out_stride = 4LL * R;
         g.bias = bias_; g.S = Sc; g.accumulate = accumulate;
         g.perm = perm_; g.m_tiles = Mpad_ / GM_BM;
-        dim3 grid((unsigned)(g.m_tiles * ((Sc + GM_BS - 1) / GM_BS)));
         const double flops = 2.0 * M * (double)K * 4.0 * Sc;
         const bool t = timing_on();
         size_t a = 0;
         if (t) a = span_begin();
-        compose_gemm_kernel<<<grid, GM_THREADS, gemm_smem_bytes(K), stream>>>(g);
+        auto go = [&](auto cfg) {
+            using C = decltype(cfg);
+            dim3 grid((unsigned)(g.m_tiles * ((Sc + C::BS - 1) / C::BS)));
+            compose_gemm_kernel<C><<<grid, C::THREADS, C::smem_bytes(K), stream>>>(g);
+        };
+        switch (gemm_variant) {
+            case 1: go(GemmCfg<4, 4, 16, 4>{}); break;
+            case 2: go(GemmCfg<4, 4, 32, 3>{}); break;
+            case 3: go(GemmCfg<4, 2, 32, 3>{}); break;
+            case 4: go(GemmCfg<4, 2, 16, 4, 16, 2>{}); break;
+            case 5: go(GemmCfg<4, 2, 16, 3, 16, 2>{}); break;
+            case 6: go(GemmCfg<4, 1, 16, 4, 8, 3>{}); break;
+            default: go(GemmDefault{}); break;
+        }
         ++stats.n_launches;
         CK(cudaGetLastError());
         if (t) span_end(a, 0, flops);
@@ -377,7 +390,7 @@ struct am_handle {
         size_t c = (size_t)(gib * (1ull << 30)) / per;
         c = std::max<size_t>(c, 1024);
         c = std::min<size_t>(c, 1u << 22);
-        return (c / GM_BS) * GM_BS;
+        return (c / 32) * 32;
     }
 
     void ensure_chunk_scratch(size_t Sc)
@@ -473,7 +486,7 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
     }
     for (int l = 1; l < D; ++l) {
         const int K = h->n[l], M = h->n[l + 1];
-        const int Kp = (K + GM_BK - 1) / GM_BK * GM_BK, Mp = (M + GM_BM - 1) / GM_BM * GM_BM;
+        const int Kp = (K + GM_KPAD - 1) / GM_KPAD * GM_KPAD, Mp = (M + GM_BM - 1) / GM_BM * GM_BM;
         h->Kpad[l] = Kp; h->Mpad[l] = Mp;
         auto w = fetch_real(W[l], (size_t)M * K, h->f64);
         auto b = fetch_real(B[l], (size_t)M, h->f64);
@@ -499,7 +512,7 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
         if (th == 0 && tw == 0) continue;
         auto w = fetch_real(TMp[t], (size_t)th * tw, h->f64);
         upload(h->TM[t], w.data(), w.size() * 8, h->stream);
-        const int Kp = (tw + GM_BK - 1) / GM_BK * GM_BK, Mp = (th + GM_BM - 1) / GM_BM * GM_BM;
+        const int Kp = (tw + GM_KPAD - 1) / GM_KPAD * GM_KPAD, Mp = (th + GM_BM - 1) / GM_BM * GM_BM;
         h->tm_Mpad[t] = Mp;
         std::vector<double> wt((size_t)Kp * Mp, 0.0);
         for (int m = 0; m < th; ++m)
@@ -858,9 +871,21 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         {
             int kmax = 3;
             for (int l = 1; l <= h->D; ++l) kmax = std::max(kmax, h->n[l]);
-            const size_t need = gemm_smem_bytes(kmax);
-            if (need > 227 * 1024) throw CudaFail{"hidden layers wider than ~31000 neurons are not supported"};
-            CK(cudaFuncSetAttribute(compose_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            if (const char *e = getenv("AM_B200_GEMM_VARIANT")) h->gemm_variant = atoi(e);
+            auto prep = [&](auto cfg, auto kern) {
+                const size_t need = decltype(cfg)::smem_bytes(kmax);
+                if (need > 227 * 1024) throw CudaFail{"hidden layers this wide are not supported by the composition kernel"};
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            };
+            switch (h->gemm_variant) {
+                case 1: prep(GemmCfg<4, 4, 16, 4>{}, compose_gemm_kernel<GemmCfg<4, 4, 16, 4>>); break;
+                case 2: prep(GemmCfg<4, 4, 32, 3>{}, compose_gemm_kernel<GemmCfg<4, 4, 32, 3>>); break;
+                case 3: prep(GemmCfg<4, 2, 32, 3>{}, compose_gemm_kernel<GemmCfg<4, 2, 32, 3>>); break;
+                case 4: prep(GemmCfg<4, 2, 16, 4, 16, 2>{}, compose_gemm_kernel<GemmCfg<4, 2, 16, 4, 16, 2>>); break;
+                case 5: prep(GemmCfg<4, 2, 16, 3, 16, 2>{}, compose_gemm_kernel<GemmCfg<4, 2, 16, 3, 16, 2>>); break;
+                case 6: prep(GemmCfg<4, 1, 16, 4, 8, 3>{}, compose_gemm_kernel<GemmCfg<4, 1, 16, 4, 8, 3>>); break;
+                default: prep(GemmDefault{}, compose_gemm_kernel<GemmDefault>); break;
+            }
         }
     } catch (const CudaFail &f) {
         g_create_error = "am_create: " + f.msg;

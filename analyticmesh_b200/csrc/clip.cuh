@@ -66,7 +66,7 @@ __device__ __forceinline__ void solve3(const double *r0, const double *r1, const
 
 constexpr int CLIP_WARPS = 8;
 
-__global__ void __launch_bounds__(CLIP_WARPS * 32) clip_kernel(const ClipArgs a)
+__global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs a)
 {
     __shared__ double s_pl[CLIP_WARPS][VSLOTS][4];   // plane of every polygon edge
     __shared__ double s_vx[CLIP_WARPS][VSLOTS][3];   // vertex j = edge j  ^  edge j+1
@@ -128,24 +128,52 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32) clip_kernel(const ClipArgs a)
     const int C = a.L + a.E;
     int n_inconsistent = 0;
     bool overflow = false;
+    // row of constraint c for this state (layer 1 rows are shared, extra constraints follow the neurons)
+    auto row_of = [&](int c) -> const double * {
+        return (c < a.n1) ? a.P1 + (size_t)c * 4
+             : (c < a.L)  ? a.P + (size_t)s * a.p_stride + (size_t)(c - a.n1) * 4
+                          : a.extra + (size_t)(c - a.L) * 4;
+    };
+    double2 nlo = make_double2(0, 0), nhi = make_double2(0, 0);   // software prefetch of the next 32 rows
+    if (lane < C) {
+        const double *r = row_of(lane);
+        nlo = *reinterpret_cast<const double2 *>(r);
+        nhi = *reinterpret_cast<const double2 *>(r + 2);
+    }
     for (int base = 0; base < C && k > 0 && !overflow; base += 32) {
         const int c = base + lane;
+        const double2 lo = nlo, hi = nhi;
+        if (c + 32 < C) {
+            const double *r = row_of(c + 32);
+            nlo = *reinterpret_cast<const double2 *>(r);
+            nhi = *reinterpret_cast<const double2 *>(r + 2);
+        }
         double p[4] = {0, 0, 0, 0};
         double rs = 0.0;
         bool cuts = false;
         if (c < C) {
-            const double *row = (c < a.n1) ? a.P1 + (size_t)c * 4
-                              : (c < a.L)  ? a.P + (size_t)s * a.p_stride + (size_t)(c - a.n1) * 4
-                                           : a.extra + (size_t)(c - a.L) * 4;
-            const double2 lo = *reinterpret_cast<const double2 *>(row);
-            const double2 hi = *reinterpret_cast<const double2 *>(row + 2);
             double sg = 1.0;
             if (c < a.L && ((key[c >> 5] >> (c & 31)) & 1u)) sg = -1.0;
             p[0] = sg * lo.x; p[1] = sg * lo.y; p[2] = sg * hi.x; p[3] = sg * hi.y;
-            rs = rsqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+            // any_j (d_j * rs > EPS)  <=>  (max_j d_j) * rs > EPS  because rs >= 0 and the product is
+            // monotone; rs (a double rsqrt) is only needed when some vertex is on the positive side
+            double dmax = -INFINITY;
+            bool nan_seen = false;
             for (int j = 0; j < k; ++j) {
                 const double d = p[0] * vx[j][0] + p[1] * vx[j][1] + p[2] * vx[j][2] + p[3];
-                cuts |= (d * rs > EPS_FEAS);
+                dmax = fmax(dmax, d);
+                nan_seen |= (d != d);
+            }
+            if (dmax > 0.0 || nan_seen) {
+                rs = rsqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+                if (nan_seen) {   // keep the reference's NaN semantics exactly: test every vertex
+                    for (int j = 0; j < k; ++j) {
+                        const double d = p[0] * vx[j][0] + p[1] * vx[j][1] + p[2] * vx[j][2] + p[3];
+                        cuts |= (d * rs > EPS_FEAS);
+                    }
+                } else {
+                    cuts = (dmax * rs > EPS_FEAS);
+                }
             }
         }
         unsigned todo = __ballot_sync(FULL, cuts);

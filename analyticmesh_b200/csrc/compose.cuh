@@ -28,18 +28,29 @@
 namespace amb {
 
 constexpr int GM_BM = 128;
-constexpr int GM_BS = 32;                 // states per tile
-constexpr int GM_BN = GM_BS * 4;          // 128 columns
-constexpr int GM_BK = 16;
-constexpr int GM_STAGES = 4;
-constexpr int GM_THREADS = 256;           // 8 warps as 4 (m) x 2 (n); warp tile 32 x 64 = 4 x 8 DMMA tiles
 constexpr int GM_AS_STRIDE = GM_BM + 4;   // +32 B per k-row: fragment loads and cp.async writes conflict-free
-constexpr int GM_BS_STRIDE = GM_BN + 4;
-constexpr int GM_SMEM_A = GM_BK * GM_AS_STRIDE;          // doubles per stage
-constexpr int GM_SMEM_B = GM_BK * GM_BS_STRIDE;
-constexpr size_t GM_SMEM_TILES = size_t(GM_STAGES) * (GM_SMEM_A + GM_SMEM_B) * sizeof(double);
-// + mask words of the 32 states of the tile: 32 x nw uint32, nw = ceil((bit0 % 32 + K) / 32) + 1 <= K/32 + 4
-inline size_t gemm_smem_bytes(int K) { return GM_SMEM_TILES + size_t(GM_BS) * (K / 32 + 4) * sizeof(uint32_t); }
+
+// tile configuration: WM x WN warps, BK rows per pipeline stage, ST stages, BS states per tile,
+// MINB resident CTAs per SM
+template <int WM_, int WN_, int BK_, int ST_, int BS_ = 32, int MINB_ = 1>
+struct GemmCfg {
+    static constexpr int WM = WM_, WN = WN_, BK = BK_, ST = ST_, BS = BS_, MINB = MINB_;
+    static constexpr int BN = BS * 4;                   // columns of the tile
+    static constexpr int BS_STRIDE = BN + 4;
+    static constexpr int THREADS = WM * WN * 32;
+    static constexpr int MI = GM_BM / WM / 8;           // DMMA tiles per warp along m
+    static constexpr int NJ = BN / WN / 8;              // ... along n
+    static constexpr int SMEM_A = BK * GM_AS_STRIDE;    // doubles per stage
+    static constexpr int SMEM_B = BK * BS_STRIDE;
+    static constexpr int CHUNKS_A = BK * 64 / THREADS;  // 16-byte cp.async per thread per stage
+    static constexpr int CHUNKS_B = BK * BS * 2 / THREADS;
+    static constexpr size_t TILE_BYTES = size_t(ST) * (SMEM_A + SMEM_B) * sizeof(double);
+    // + mask words of the BS states of the tile: BS x nw uint32, nw = ceil((bit0 % 32 + K) / 32) + 1 <= K/32 + 4
+    static size_t smem_bytes(int K) { return TILE_BYTES + size_t(BS) * (K / 32 + 4) * sizeof(uint32_t); }
+};
+using GemmDefault = GemmCfg<4, 2, 16, 4>;
+constexpr int GM_BK = 16;                 // k padding unit of the staged weights (multiple of every BK/2)
+constexpr int GM_KPAD = 32;               // weights are zero padded to a multiple of this many k rows
 
 struct GemmArgs {
     const double *Wt;           // [Kpad][Mpad], k-major, zero padded
@@ -77,25 +88,26 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmArgs a)
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) compose_gemm_kernel(const GemmArgs a)
 {
     extern __shared__ __align__(16) double smem[];
-    double *As = smem;                               // [STAGES][BK][AS_STRIDE]
-    double *Bs = smem + GM_STAGES * GM_SMEM_A;       // [STAGES][BK][BS_STRIDE]
-    uint32_t *smask = reinterpret_cast<uint32_t *>(smem + GM_STAGES * (GM_SMEM_A + GM_SMEM_B));
+    double *As = smem;                               // [ST][BK][AS_STRIDE]
+    double *Bs = smem + C::ST * C::SMEM_A;           // [ST][BK][BS_STRIDE]
+    uint32_t *smask = reinterpret_cast<uint32_t *>(smem + C::ST * (C::SMEM_A + C::SMEM_B));
 
     const int tid = threadIdx.x;
     const int m0 = (blockIdx.x % a.m_tiles) * GM_BM;      // m fastest: CTAs that share a B tile are co-resident
-    const int s0 = (blockIdx.x / a.m_tiles) * GM_BS;
+    const int s0 = (blockIdx.x / a.m_tiles) * C::BS;
     const int S = a.S;
-    const int KT = (a.K + GM_BK - 1) / GM_BK;
+    const int KT = (a.K + C::BK - 1) / C::BK;
     const int lane = tid & 31, warp = tid >> 5;
 
     // ---- mask words of the tile's 32 states -> shared memory (one coalesced pass) ---------------
     // smask[sl][j] = key word (bit0/32 + j) of the state in tile slot sl; nw = words that cover the layer
     const int w0 = a.bit0 >> 5, sh = a.bit0 & 31;
     const int nw = (sh + a.K + 31) / 32 + 1;
-    for (int i = tid; i < GM_BS * nw; i += GM_THREADS) {
+    for (int i = tid; i < C::BS * nw; i += C::THREADS) {
         const int sl = i / nw, j = i - sl * nw;
         const int slot = s0 + sl;
         uint32_t v = 0;
@@ -107,31 +119,33 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
     }
 
     // ---- producer mapping ------------------------------------------------------------------
-    // A: 16 rows x 1 KiB = 1024 chunks of 16 B, 4 per thread (rows of 64 chunks, coalesced)
-    // B: per state 16 k x 32 B = 512 B contiguous in global; warp w stages tile slots w, w+8, w+16, w+24
-    const int bk = lane >> 1, bhalf = lane & 1;      // k row and (xy | zc) half handled by this lane
-    long long bbase[4];                              // element offset of the state's rows, -1 = empty slot
+    // A: BK rows x 1 KiB = BK*64 chunks of 16 B (rows of 64 chunks, coalesced)
+    // B: chunk c -> tile slot c / (2 BK), k row (c % (2 BK)) / 2, (xy | zc) half c % 2: a state's BK rows
+    //    are BK * 32 B contiguous in global memory
+    long long bbase[C::CHUNKS_B];                    // element offset of the state's rows, -1 = empty slot
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int slot = s0 + warp + 8 * i;
+    for (int i = 0; i < C::CHUNKS_B; ++i) {
+        const int slot = s0 + (tid + i * C::THREADS) / (2 * C::BK);
         bbase[i] = (slot < S) ? (long long)(a.perm ? a.perm[slot] : slot) * a.b_stride : -1;
     }
     __syncthreads();                                 // smask visible
 
     auto load_stage = [&](int kt, int slot) {
-        double *as = As + slot * GM_SMEM_A;
-        double *bs = Bs + slot * GM_SMEM_B;
-        const int k0 = kt * GM_BK;
+        double *as = As + slot * C::SMEM_A;
+        double *bs = Bs + slot * C::SMEM_B;
+        const int k0 = kt * C::BK;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = tid + i * GM_THREADS;      // 0..1023
+        for (int i = 0; i < C::CHUNKS_A; ++i) {
+            const int c = tid + i * C::THREADS;
             const int row = c >> 6, col = (c & 63) * 2;
             cp_async16(as + row * GM_AS_STRIDE + col, a.Wt + (size_t)(k0 + row) * a.Mpad + m0 + col, 16);
         }
         const int pos = sh + k0;                     // bit position of the slab inside the staged words
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int sl = warp + 8 * i;
+        for (int i = 0; i < C::CHUNKS_B; ++i) {
+            const int c = tid + i * C::THREADS;
+            const int sl = c / (2 * C::BK), r = c % (2 * C::BK);
+            const int bk = r >> 1, bhalf = r & 1;
             const int k = k0 + bk;
             const uint32_t *mw = smask + sl * nw + (pos >> 5);
             const uint32_t bits = __funnelshift_r(mw[0], mw[1], pos & 31);
@@ -141,46 +155,46 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
                 bytes = 16;
                 src = a.Bsrc + bbase[i] + (size_t)k * 4 + bhalf * 2;
             }
-            cp_async16(bs + bk * GM_BS_STRIDE + sl * 4 + bhalf * 2, src, bytes);
+            cp_async16(bs + bk * C::BS_STRIDE + sl * 4 + bhalf * 2, src, bytes);
         }
     };
 
-    // ---- consumer mapping: warp (wm, wn) owns rows [32 wm, +32) x columns [64 wn, +64) ------------
+    // ---- consumer mapping: warp (wm, wn) owns rows [8 MI wm, +8 MI) x columns [8 NJ wn, +8 NJ) -------
     // DMMA fragments (PTX m8n8k4.f64): a = A[row = lane/4][k = lane%4], b = B[k = lane%4][col = lane/4],
     //                                   c0,c1 = C[row = lane/4][col = 2 (lane%4) + {0,1}]
-    const int wm = warp & 3, wn = warp >> 2;
+    const int wm = warp % C::WM, wn = warp / C::WM;
     const int fr = lane >> 2, fk = lane & 3;
-    double acc[4][8][2];
+    double acc[C::MI][C::NJ][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < C::MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
-    for (int st = 0; st < GM_STAGES - 1; ++st) {
+    for (int st = 0; st < C::ST - 1; ++st) {
         if (st < KT) load_stage(st, st);
         cp_async_commit();
     }
 
     for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<GM_STAGES - 2>();
+        cp_async_wait<C::ST - 2>();
         __syncthreads();
-        if (kt + GM_STAGES - 1 < KT) load_stage(kt + GM_STAGES - 1, (kt + GM_STAGES - 1) % GM_STAGES);
+        if (kt + C::ST - 1 < KT) load_stage(kt + C::ST - 1, (kt + C::ST - 1) % C::ST);
         cp_async_commit();
 
-        const double *as = As + (kt % GM_STAGES) * GM_SMEM_A + fk * GM_AS_STRIDE + wm * 32 + fr;
-        const double *bs = Bs + (kt % GM_STAGES) * GM_SMEM_B + fk * GM_BS_STRIDE + wn * 64 + fr;
+        const double *as = As + (kt % C::ST) * C::SMEM_A + fk * GM_AS_STRIDE + wm * (8 * C::MI) + fr;
+        const double *bs = Bs + (kt % C::ST) * C::SMEM_B + fk * C::BS_STRIDE + wn * (8 * C::NJ) + fr;
 #pragma unroll
-        for (int kk = 0; kk < GM_BK / 4; ++kk) {
-            double av[4], bv[8];
+        for (int kk = 0; kk < C::BK / 4; ++kk) {
+            double av[C::MI], bv[C::NJ];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = as[kk * 4 * GM_AS_STRIDE + i * 8];
+            for (int i = 0; i < C::MI; ++i) av[i] = as[kk * 4 * GM_AS_STRIDE + i * 8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bv[j] = bs[kk * 4 * GM_BS_STRIDE + j * 8];
+            for (int j = 0; j < C::NJ; ++j) bv[j] = bs[kk * 4 * C::BS_STRIDE + j * 8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < C::MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+                for (int j = 0; j < C::NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
         }
     }
     cp_async_wait<0>();
@@ -189,14 +203,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1) compose_gemm_kernel(const GemmA
     // columns 2 fk, 2 fk + 1 of an 8-column block = components comp0, comp0+1 of state (block*2 + fk/2)
     const int comp0 = (fk & 1) * 2;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int slot = s0 + wn * 16 + j * 2 + (fk >> 1);
+    for (int j = 0; j < C::NJ; ++j) {
+        const int slot = s0 + wn * (2 * C::NJ) + j * 2 + (fk >> 1);
         if (slot >= S) continue;
         const int s = a.perm ? a.perm[slot] : slot;
         double *dst = a.out + (size_t)s * a.out_stride + comp0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = m0 + wm * 32 + i * 8 + fr;
+        for (int i = 0; i < C::MI; ++i) {
+            const int m = m0 + wm * (8 * C::MI) + i * 8 + fr;
             if (m >= a.M) continue;
             double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
             if (a.bias != nullptr && comp0 == 2) v.y += a.bias[m];

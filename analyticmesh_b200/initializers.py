@@ -101,3 +101,116 @@ def states_of(model, points):
         states = torch.cat([(s > 0) for s in model.outputs_list], dim=1)
         model.outputs_list = []
     return states
+
+
+class _Corr:
+    """Correlation of the recent error history with time (reference main.py:94-107): a value near 1
+    means the error is still going down steadily; it is used as a divergence / stall detector."""
+
+    def __init__(self, hist_len):
+        import numpy as np
+        self.np = np
+        self.hist_len = hist_len
+        self.t = np.arange(hist_len)
+        self.hist = []
+
+    def push(self, value):
+        if not self.hist:
+            self.hist = [value] * self.hist_len
+            return 1.0
+        self.hist = [value] + self.hist[:-1]
+        with self.np.errstate(all="ignore"):
+            return float(self.np.corrcoef(self.np.asarray(self.hist), self.t)[0, 1])
+
+
+def sphere_tracing(model, iso, init_num, step_size_max, step_size_mul, step_size_min, w_extra_constraints,
+                   b_extra_constraints, init_ball_radius, avg_eps, hist_len, corr_min, time_out, generator=None,
+                   verbose=False):
+    """Newton-like marching x <- x - step * f * grad f from random points in the ball, restarting with a
+    smaller step when the mean error stops decreasing (behaviour of reference main.py:112-177; suited to
+    SDF-like fields).  May return fewer than `init_num` points."""
+    import numpy as np
+    device = _device_of(model)
+    step, t0 = step_size_max, time.time()
+    corr = _Corr(hist_len)
+    while True:
+        pts = init_within_ball(init_num, init_ball_radius, w_extra_constraints, b_extra_constraints, generator).to(device)
+        prev_err, done = 1e10, False
+        while True:
+            pts = pts.detach().requires_grad_(True)
+            pred = model(pts) - iso
+            err = pred.abs().mean()
+            c = corr.push(err.item())
+            if verbose:
+                print(f'(cuam) (sphere_init) avg_err = {err}, corr = {c}, step_size = {step}')
+            if time.time() - t0 > time_out:
+                raise Exception(f'Error: sphere_tracing cannot find solution within time={time_out}!')
+            if err > prev_err * 2 or not torch.isfinite(err) or err > 100 or c < corr_min or not np.isfinite(c):
+                step *= step_size_mul
+                if step < step_size_min:
+                    raise Exception('Error: sphere_tracing cannot find solution!')
+                break
+            prev_err = err
+            if err < avg_eps:
+                done = True
+                break
+            grad = torch.autograd.grad(pred, pts, grad_outputs=torch.ones_like(pred))[0]
+            with torch.no_grad():
+                pts = pts - step * pred * grad
+        if done:
+            break
+    pts = pts.detach()
+    pts = pts[(pts ** 2).sum(dim=1) < init_ball_radius ** 2]
+    return constraints_filter(pts, w_extra_constraints, b_extra_constraints)
+
+
+def gradient_descent(model, iso, init_num, lr_max, lr_mul, lr_min, corr_min, hist_len, loss_type, optimizer_type,
+                     accept_bad, w_extra_constraints, b_extra_constraints, init_ball_radius, batch_mul, avg_eps,
+                     time_out, generator=None, verbose=False):
+    """Minimise |f - iso| over the point coordinates with Adam/SGD, shrinking the learning rate when the
+    error history stalls (behaviour of reference main.py:180-249).  Returns exactly `init_num` points."""
+    device = _device_of(model)
+    if loss_type == 'smooth_l1':
+        scale = avg_eps * 10
+        loss_fn = lambda x: (torch.nn.functional.smooth_l1_loss(x / scale, torch.zeros_like(x), reduction='none') * scale).mean()  # noqa: E731
+    elif loss_type == 'l1':
+        loss_fn = lambda x: x.abs().mean()  # noqa: E731
+    elif loss_type == 'l2':
+        loss_fn = lambda x: (x ** 2).mean()  # noqa: E731
+    else:
+        raise Exception(f"Error: No such {loss_type}")
+    t0 = time.time()
+    found = torch.zeros([0, 3], device=device)
+    while found.size(0) < init_num:
+        p = init_within_ball(int((init_num - found.size(0)) * batch_mul), init_ball_radius, w_extra_constraints,
+                             b_extra_constraints, generator).to(device).requires_grad_()
+        if optimizer_type == 'adam':
+            opt = torch.optim.Adam([p], lr=lr_max)
+        elif optimizer_type == 'sgd':
+            opt = torch.optim.SGD([p], lr=lr_max, momentum=0.9)
+        else:
+            raise Exception(f"Error: No such {optimizer_type}")
+        corr = _Corr(hist_len)
+        err, pred = 1e9, None
+        while err > avg_eps:
+            if pred is not None:
+                opt.zero_grad()
+                loss_fn(pred).backward()
+                opt.step()
+            pred = model(p) - iso
+            err = pred.abs().mean().item()
+            c = corr.push(err)
+            if verbose:
+                print(f'(cuam) (gradient_descent) pred_err_mean = {err:.2e} | corr = {c:.2e}')
+            if time.time() - t0 > time_out:
+                raise Exception(f'Error: gradient_descent cannot find solution within {time_out} seconds!')
+            if c < corr_min:
+                corr = _Corr(hist_len)
+                for g in opt.param_groups:
+                    g['lr'] *= lr_mul
+                if opt.param_groups[0]['lr'] < lr_min:
+                    break
+        if opt.param_groups[0]['lr'] >= lr_min or accept_bad:
+            q = constraints_filter(p.detach(), w_extra_constraints, b_extra_constraints)
+            found = torch.cat([found, q[:init_num - found.size(0)]], dim=0)
+    return found
