@@ -298,13 +298,8 @@ struct am_handle {
             dim3 grid((unsigned)(g.m_tiles * ((Sc + C::BS - 1) / C::BS)));
             compose_gemm_kernel<C><<<grid, C::THREADS, C::smem_bytes(K), stream>>>(g);
         };
-        switch (gemm_variant) {
-            case 1: go(GemmCfg<4, 4, 16, 4>{}); break;
-            case 2: go(GemmCfg<4, 4, 32, 3>{}); break;
-            case 3: go(GemmCfg<4, 2, 32, 3>{}); break;
-            case 4: go(GemmCfg<4, 2, 16, 4, 16, 2>{}); break;
-            case 5: go(GemmCfg<4, 2, 16, 3, 16, 2>{}); break;
-            case 6: go(GemmCfg<4, 1, 16, 4, 8, 3>{}); break;
+        switch (gemm_variant) {   // AM_B200_GEMM_VARIANT: tuning knob, see DESIGN.md section 4
+            case 1: go(GemmWide{}); break;
             default: go(GemmDefault{}); break;
         }
         ++stats.n_launches;
@@ -878,12 +873,7 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             };
             switch (h->gemm_variant) {
-                case 1: prep(GemmCfg<4, 4, 16, 4>{}, compose_gemm_kernel<GemmCfg<4, 4, 16, 4>>); break;
-                case 2: prep(GemmCfg<4, 4, 32, 3>{}, compose_gemm_kernel<GemmCfg<4, 4, 32, 3>>); break;
-                case 3: prep(GemmCfg<4, 2, 32, 3>{}, compose_gemm_kernel<GemmCfg<4, 2, 32, 3>>); break;
-                case 4: prep(GemmCfg<4, 2, 16, 4, 16, 2>{}, compose_gemm_kernel<GemmCfg<4, 2, 16, 4, 16, 2>>); break;
-                case 5: prep(GemmCfg<4, 2, 16, 3, 16, 2>{}, compose_gemm_kernel<GemmCfg<4, 2, 16, 3, 16, 2>>); break;
-                case 6: prep(GemmCfg<4, 1, 16, 4, 8, 3>{}, compose_gemm_kernel<GemmCfg<4, 1, 16, 4, 8, 3>>); break;
+                case 1: prep(GemmWide{}, compose_gemm_kernel<GemmWide>); break;
                 default: prep(GemmDefault{}, compose_gemm_kernel<GemmDefault>); break;
             }
         }

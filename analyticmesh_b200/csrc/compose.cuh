@@ -18,8 +18,8 @@
 // (tools/dmma_exact.cu: 128000/128000), so every output is still exactly the value the CPU
 // restatement used by the parity tests computes.
 //
-// Tile: 128 (m) x 32 states (= 128 columns) x 16 (k); 256 threads = 8 warps as 4 x 2, warp tile
-// 32 x 64 = 4 x 8 DMMA tiles; 4-stage cp.async pipeline, ~134 KiB shared memory, one CTA per SM.
+// Tile: 128 (m) x 16 states (= 64 columns) x 16 (k); 256 threads = 8 warps as 4 x 2, warp tile
+// 32 x 32 = 4 x 4 DMMA tiles; 4-stage cp.async pipeline, ~100 KiB shared memory, two CTAs per SM.
 // The mask words of the tile's states are staged in shared memory once, so the producer never waits
 // on a dependent global load.
 #pragma once
@@ -48,7 +48,12 @@ struct GemmCfg {
     // + mask words of the BS states of the tile: BS x nw uint32, nw = ceil((bit0 % 32 + K) / 32) + 1 <= K/32 + 4
     static size_t smem_bytes(int K) { return TILE_BYTES + size_t(BS) * (K / 32 + 4) * sizeof(uint32_t); }
 };
-using GemmDefault = GemmCfg<4, 2, 16, 4>;
+// Measured on B200 at 8x512 (tools/run_case.py mlp8x512s, whole march, TFLOP/s of this kernel):
+//   128 x 16 states, 2 CTAs/SM (default) 31.2 | 128 x 32 states, 1 CTA/SM 27.7 | 16 warps 27.3 |
+//   BK 32 / 3 stages 28.5 | 128 x 8 states 28.5.   Two co-resident CTAs hide each other's prologue,
+//   epilogue and barrier phases, which a single CTA per SM exposes.
+using GemmDefault = GemmCfg<4, 2, 16, 4, 16, 2>;
+using GemmWide = GemmCfg<4, 2, 16, 4, 32, 1>;
 constexpr int GM_BK = 16;                 // k padding unit of the staged weights (multiple of every BK/2)
 constexpr int GM_KPAD = 32;               // weights are zero padded to a multiple of this many k rows
 
