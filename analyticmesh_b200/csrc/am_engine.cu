@@ -132,6 +132,9 @@ struct am_handle {
     DevBuf owner, xchg;
     long long shard_owned_states = 0;
     int *h_npre = nullptr;                      // pinned
+    int *h_next = nullptr;                      // pinned: bucket histogram of the NEXT level (count_winners_kernel)
+    DevBuf next_counts;
+    bool next_valid = false;
     unsigned long long *h_counters = nullptr;   // pinned
     cudaStream_t stream = nullptr;
 
@@ -186,6 +189,9 @@ struct am_handle {
         h_counters = nullptr;
         if (h_npre) cudaFreeHost(h_npre);
         h_npre = nullptr;
+        if (h_next) cudaFreeHost(h_next);
+        h_next = nullptr;
+        next_counts.release();
     }
 
     // rows of hidden layer h for state 0 of a chunk + stride (doubles)
@@ -618,7 +624,7 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     ca.idx = idx;
     ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
     ca.counters = h->counters.as<unsigned long long>();
-    clip_kernel<<<(n + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, 0, st>>>(ca);
+    clip_kernel<<<(n + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, CLIP_RING_BYTES, st>>>(ca);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
 }
@@ -638,7 +644,7 @@ void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc)
     co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
     compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
     ++h->stats.n_launches;
-    bump_counters_kernel<<<1, 256, 0, st>>>(cnt, sc.cnt, Sc);
+    bump_counters_kernel<<<1, 32, 0, st>>>(cnt);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
 }
@@ -691,7 +697,26 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         ++h->stats.n_launches;
         CK(cudaGetLastError());
         std::vector<int> npre(D + 3, 0);
-        CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 2) * 4, cudaMemcpyDeviceToHost, st));
+        // launch sizes of this level: predicted by count_winners_kernel of the previous level (read back
+        // together with n_new), computed for the seed level, or -- fallback -- read back now
+        bool have = false;
+        if (lb == 0) {                       // seeds: every state is recomputed from layer 2 on
+            const int mine = sharded ? (int)((S - h->shard_rank + h->shard_world - 1) / h->shard_world) : (int)S;
+            for (int b = 1; b <= D; ++b) npre[b] = mine;
+            npre[D + 1] = (int)S;
+            have = true;
+        } else if (h->next_valid) {
+            int run = 0;
+            for (int b = 1; b <= D; ++b) {
+                run += h->h_next[b];
+                npre[b] = run;
+            }
+            if (!h->prev_resident)           // parents' rows are gone: everything owned is recomputed
+                for (int b = 1; b <= D; ++b) npre[b] = run;
+            npre[D + 1] = (int)S;
+            have = true;
+        }
+        if (!have) CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 2) * 4, cudaMemcpyDeviceToHost, st));
         if (sharded) CK(cudaMemsetAsync(h->xchg.p, 0, ((size_t)(S + 1) & ~size_t(1)) * (4 + VSLOTS * 4 + VSLOTS * 24), st));
         if (h->prev_resident) {
             copy_parent_rows_kernel<<<(unsigned)((S + 7) / 8), 256, 0, st>>>(
@@ -700,8 +725,10 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
             ++h->stats.n_launches;
             CK(cudaGetLastError());
         }
-        CK(cudaStreamSynchronize(st));
-        for (int b = 0; b <= D + 1; ++b) npre[b] = h->h_npre[b];
+        if (!have) {
+            CK(cudaStreamSynchronize(st));
+            for (int b = 0; b <= D + 1; ++b) npre[b] = h->h_npre[b];
+        }
         const int n_mine = npre[D];                       // states this rank composes and clips
         h->shard_owned_states += n_mine;
         h->compose_chunk(keys0, (int)S, iso, base, h->perm.as<int>(), npre.data(), sharded ? n_mine : (int)S,
@@ -710,10 +737,10 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         if (timing) t0 = h->span_begin();
         run_clip(h, lb, sharded ? n_mine : (int)S, base, flip, sharded ? h->perm.as<int>() : nullptr, sc);
         if (sharded) {   // union of the ranks' polygons: every slot is non-zero on exactly one rank
-            CK(cudaStreamSynchronize(st));
             const size_t Sp = ((size_t)S + 1) & ~size_t(1);
             const long long n32 = (long long)(Sp * (4 + VSLOTS * 4 + VSLOTS * 24) / 4);
-            if (h->shard_cb(h->shard_user, h->xchg.p, n32) != 0) throw CudaFail{"the host all-reduce callback failed"};
+            if (h->shard_cb(h->shard_user, h->xchg.p, n32, (void *)st) != 0)
+                throw CudaFail{"the host all-reduce callback failed"};
         }
         store_faces(h, lb, (int)S, sc);
         if (timing) h->span_end(t0, 2);
@@ -767,11 +794,20 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     const unsigned gb = (unsigned)((S * G + 255) / 256);
     h->dispatch_group([&](auto g) { expand_insert_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
     ++h->stats.n_launches;
-    count_winners_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a);
-    ++h->stats.n_launches;
-    CK(cudaGetLastError());
+    {
+        LayerOffs lo{};
+        lo.D = h->D;
+        for (int l = 1; l <= h->D + 1; ++l) lo.off[l] = h->off[l];
+        a.owner = h->shard_world > 1 ? h->owner.as<uint8_t>() : nullptr;
+        CK(cudaMemsetAsync(h->next_counts.p, 0, (size_t)(h->D + 3) * 4, st));
+        count_winners_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a, lo, h->next_counts.as<int>(), h->shard_rank);
+        ++h->stats.n_launches;
+        CK(cudaGetLastError());
+    }
     h->scan(h->nwin.as<uint32_t>(), h->wbase.as<uint32_t>(), (int)S, cnt + CNT_NEW);
+    CK(cudaMemcpyAsync(h->h_next, h->next_counts.p, (size_t)(h->D + 3) * 4, cudaMemcpyDeviceToHost, st));
     h->read_counters();                                   // the one host sync of the level
+    h->next_valid = true;
     const long long n_new = (long long)h->h_counters[CNT_NEW];
     if (h->n_states + n_new >= (1LL << 31) - 1) throw CudaFail{"more than 2^31 states"};
     h->ensure_states((size_t)(h->n_states + n_new));
@@ -860,8 +896,11 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         CK(cudaMallocHost(&h->h_counters, CNT_NUM * 8));
         memset(h->h_counters, 0, CNT_NUM * 8);
         if (h->D + 2 > MAX_LAYERS) throw CudaFail{"more than 62 hidden layers"};
-        CK(cudaMallocHost(&h->h_npre, (size_t)(h->D + 2) * 4));
+        CK(cudaMallocHost(&h->h_npre, (size_t)(h->D + 3) * 4));
+        CK(cudaMallocHost(&h->h_next, (size_t)(h->D + 3) * 4));
+        h->next_counts.reserve((size_t)(h->D + 3) * 4);
         if (const char *e = getenv("AM_B200_INCREMENTAL")) h->incremental = atoi(e) != 0;
+        CK(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLIP_RING_BYTES));
         h->counters.reserve(CNT_NUM * 8);
         {
             int kmax = 3;
@@ -972,6 +1011,7 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         h->n_states = 0;
         h->level_begin.clear();
         h->prev_resident = false;
+        h->next_valid = false;
         h->n_incremental_levels = 0;
         h->shard_owned_states = 0;
         {

@@ -65,9 +65,18 @@ __device__ __forceinline__ void solve3(const double *r0, const double *r1, const
 }
 
 constexpr int CLIP_WARPS = 8;
+constexpr int CLIP_DEPTH = 4;     // cp.async ring: rows of the next CLIP_DEPTH-1 iterations are in flight per lane
+constexpr size_t CLIP_RING_BYTES = size_t(CLIP_WARPS) * CLIP_DEPTH * 32 * 4 * sizeof(double);
+
+__device__ __forceinline__ void clip_cp16(void *smem, const void *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
 
 __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs a)
 {
+    extern __shared__ __align__(16) double s_ring[];  // [warp][CLIP_DEPTH][32 lanes][4]: plane rows in flight
     __shared__ double s_pl[CLIP_WARPS][VSLOTS][4];   // plane of every polygon edge
     __shared__ double s_vx[CLIP_WARPS][VSLOTS][3];   // vertex j = edge j  ^  edge j+1
     __shared__ int s_ed[CLIP_WARPS][VSLOTS];
@@ -134,20 +143,29 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
              : (c < a.L)  ? a.P + (size_t)s * a.p_stride + (size_t)(c - a.n1) * 4
                           : a.extra + (size_t)(c - a.L) * 4;
     };
-    double2 nlo = make_double2(0, 0), nhi = make_double2(0, 0);   // software prefetch of the next 32 rows
-    if (lane < C) {
-        const double *r = row_of(lane);
-        nlo = *reinterpret_cast<const double2 *>(r);
-        nhi = *reinterpret_cast<const double2 *>(r + 2);
-    }
+    // Every lane streams its own row of each 32-row block through a private shared-memory ring with
+    // cp.async, so CLIP_DEPTH-1 loads per lane are in flight without holding registers.
+    double *ring = s_ring + ((size_t)wib * CLIP_DEPTH * 32 + lane) * 4;
+    auto fetch = [&](int blk) {          // rows of block `blk` -> ring slot blk % CLIP_DEPTH
+        const int c = blk * 32 + lane;
+        if (c < C) {
+            const double *r = row_of(c);
+            double *dst = ring + (size_t)(blk % CLIP_DEPTH) * 32 * 4;
+            clip_cp16(dst, r);
+            clip_cp16(dst + 2, r + 2);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+#pragma unroll
+    for (int b = 0; b < CLIP_DEPTH - 1; ++b) fetch(b);
     for (int base = 0; base < C && k > 0 && !overflow; base += 32) {
         const int c = base + lane;
-        const double2 lo = nlo, hi = nhi;
-        if (c + 32 < C) {
-            const double *r = row_of(c + 32);
-            nlo = *reinterpret_cast<const double2 *>(r);
-            nhi = *reinterpret_cast<const double2 *>(r + 2);
-        }
+        const int blk = base >> 5;
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(CLIP_DEPTH - 2));
+        const double *mine = ring + (size_t)(blk % CLIP_DEPTH) * 32 * 4;
+        const double2 lo = *reinterpret_cast<const double2 *>(mine);
+        const double2 hi = *reinterpret_cast<const double2 *>(mine + 2);
+        fetch(blk + CLIP_DEPTH - 1);
         double p[4] = {0, 0, 0, 0};
         double rs = 0.0;
         bool cuts = false;
@@ -237,6 +255,8 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
             k = knew;
         }
     }
+
+    asm volatile("cp.async.wait_all;\n" ::);   // the loop may leave early with copies still in flight
 
     // ---- finish: validity, orientation, canonical rotation --------------------------------------
     int unbounded = 0;

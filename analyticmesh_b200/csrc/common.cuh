@@ -46,4 +46,11 @@ __host__ __device__ inline uint64_t word_mix(uint32_t w, uint32_t v)
 
 __device__ __forceinline__ uint32_t slot_fp(uint64_t h) { return uint32_t(h >> 32); }
 
+// first activation bit of every hidden layer (kernel parameter)
+constexpr int MAX_LAYERS = 64;
+struct LayerOffs {
+    int D;
+    int off[MAX_LAYERS + 2];      // off[h], h = 1..D+1
+};
+
 }  // namespace amb

@@ -274,11 +274,6 @@ __global__ void skip_hidden_identity_kernel(double *out, long long out_stride, c
 // copied from the previous level's plane buffer (kept resident) and only layers > l_e are recomputed.
 // States are bucketed by b = l_e (1 for seeds and for children whose parent rows are gone); the
 // launch of fc layer h works on the prefix of the bucket-sorted permutation with b <= h.
-constexpr int MAX_LAYERS = 64;
-struct LayerOffs {
-    int D;
-    int off[MAX_LAYERS + 2];      // off[h], h = 1..D+1
-};
 
 // Sharded mode: a state owned by another rank goes to bucket D+1, which no launch touches.
 __global__ void classify_kernel(const int *via_edge, const int *parent, int lb, int S, int prev_lb, int prev_S,

@@ -155,15 +155,28 @@ __global__ void expand_insert_kernel(const LevelArgs a)
 }
 
 // phase 2a: winners per parent (thread per parent)
-__global__ void count_winners_kernel(const LevelArgs a)
+// Also histograms the children by the hidden layer of their flipped neuron (bucket of the NEXT level's
+// incremental composition, compose.cuh classify_kernel) so that the host learns the next level's launch
+// sizes from the same read-back as n_new.  Sharded mode: only children this rank will own are counted.
+__global__ void count_winners_kernel(const LevelArgs a, LayerOffs lo, int *next_counts, int rank)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.S) return;
     uint32_t n = 0;
+    const long long fo = a.face_off[a.lb + s];
+    const bool mine = (a.owner == nullptr) || (a.owner[a.lb + s] == rank);
     for (int j = 0; j < VSLOTS; ++j) {
         const int slot = a.cand_slot[(size_t)s * VSLOTS + j];
         if (slot == NO_SLOT) continue;
-        if (uint32_t(a.table.slots[slot]) == (CAND_TAG | cand_index(s, j))) ++n;
+        if (uint32_t(a.table.slots[slot]) == (CAND_TAG | cand_index(s, j))) {
+            ++n;
+            if (mine) {
+                const int e = a.face_edges[fo + j];
+                int b = 1;
+                while (b < lo.D && e >= lo.off[b + 1]) ++b;
+                atomicAdd(next_counts + b, 1);
+            }
+        }
     }
     a.nwin[s] = n;
 }

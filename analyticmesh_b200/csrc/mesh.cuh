@@ -89,6 +89,7 @@ __global__ void compact_faces_kernel(const CompactArgs a)
     if (lane == 0) {
         a.face_off[a.sid0 + s] = base;
         if (s == a.S - 1) a.face_off[a.sid0 + s + 1] = base + k;
+        if (k > 0) atomicAdd(a.counters + CNT_FACES, 1ull);
     }
     if (lane < k) {
         a.face_edges[base + lane] = a.edges[(size_t)s * VSLOTS + lane];
@@ -98,20 +99,10 @@ __global__ void compact_faces_kernel(const CompactArgs a)
     }
 }
 
-// counters[dst] += counters[src]  (+ count faces of the chunk)
-__global__ void bump_counters_kernel(unsigned long long *counters, const int *cnt, int S)
+// running corner total += corners of the chunk just compacted (after every block has read the old base)
+__global__ void bump_counters_kernel(unsigned long long *counters)
 {
-    __shared__ unsigned int faces;
-    if (threadIdx.x == 0) faces = 0;
-    __syncthreads();
-    unsigned int mine = 0;
-    for (int i = threadIdx.x; i < S; i += blockDim.x) mine += (cnt[i] > 0);
-    atomicAdd(&faces, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        counters[CNT_CORNERS] += counters[CNT_CHUNK_CORNERS];
-        counters[CNT_FACES] += faces;
-    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) counters[CNT_CORNERS] += counters[CNT_CHUNK_CORNERS];
 }
 
 // ---- stitching ------------------------------------------------------------------------------

@@ -265,19 +265,19 @@ def mesh():
     return v, fs, fi
 
 
-ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
 _shard_cb = None   # keeps the ctypes callback alive
 
 
 def set_shard(rank, world, allreduce):
-    """Spread ONE march over `world` processes (one GPU each).  `allreduce(device_ptr, n_int32)` must sum
-    the int32 buffer over all ranks in place and return after the result is visible on the device; see
+    """Spread ONE march over `world` processes (one GPU each).  `allreduce(device_ptr, n_int32, stream)` must
+    sum the int32 buffer over all ranks in place, ordered on the given CUDA stream; see
     analyticmesh_b200.parallel.make_allreduce for the torch.distributed implementation."""
     global _shard_cb
 
-    def _cb(_user, ptr, n):
+    def _cb(_user, ptr, n, stream):
         try:
-            allreduce(ptr, n)
+            allreduce(ptr, n, stream)
             return 0
         except Exception as e:  # noqa: BLE001 - reported through the C ABI as a failed callback
             print(f"(cuam) all-reduce callback failed: {e!r}")

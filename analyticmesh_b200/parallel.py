@@ -26,15 +26,20 @@ def make_allreduce(group=None, device=None):
     and NCCL is used; device == 'cpu': `ptr` is host memory (gloo) -- used by the CPU tests."""
     is_cpu = device is not None and torch.device(device).type == "cpu"
 
-    def allreduce(ptr, n):
+    def allreduce(ptr, n, stream=None):
         if is_cpu:
             buf = (ctypes.c_int32 * n).from_address(ptr)
             t = torch.from_numpy(np.frombuffer(buf, dtype=np.int32))
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
             return
         t = torch.as_tensor(_DevMem(ptr, n), device=device if device is not None else "cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        torch.cuda.current_stream().synchronize()
+        if stream:
+            # enqueue the collective in order on the engine's stream: no host synchronisation
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            torch.cuda.current_stream().synchronize()
 
     return allreduce
 

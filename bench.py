@@ -232,10 +232,11 @@ def main():
     d2h = 0
     for _ in range(args.steps):
         st = march(host)
-        cuam.CombineMesh(scale=1.0, center=[0.0, 0.0, 0.0])
-        st = cuam.stats()
+        if rank == 0:   # the mesh is replicated: one rank stitches it and reads it back
+            cuam.CombineMesh(scale=1.0, center=[0.0, 0.0, 0.0])
+            st = cuam.stats()
+            d2h = st["n_vertices"] * 24 + st["n_corners"] * 4 + (st["n_states"] + 1) * 8
         e_faces += st["n_faces"]
-        d2h = st["n_vertices"] * 24 + st["n_corners"] * 4 + (st["n_states"] + 1) * 8
     e1.record()
     barrier()
     e_dt = e0.elapsed_time(e1) * 1e-3
@@ -244,11 +245,13 @@ def main():
 
     # export once (not timed in `value`): the reference's export_time phase
     t0 = time.time()
-    ply = f"/tmp/am_b200_bench_rank{rank}.ply"
-    cuam.ExportMesh(file_path=ply, is_polymesh=True, is_float32=True)
-    export_time = time.time() - t0
-    ply_bytes = os.path.getsize(ply)
-    os.remove(ply)
+    export_time, ply_bytes = 0.0, 0
+    if rank == 0:
+        ply = f"/tmp/am_b200_bench_rank{rank}.ply"
+        cuam.ExportMesh(file_path=ply, is_polymesh=True, is_float32=True)
+        export_time = time.time() - t0
+        ply_bytes = os.path.getsize(ply)
+        os.remove(ply)
 
     if world > 1:
         t = torch.tensor([dt, e_dt], dtype=torch.float64, device=dev)

@@ -92,9 +92,10 @@ void am_destroy(am_handle *h);
  * rank only (children inherit the owner of their parent, so the parent's plane rows are local);
  * once per BFS level the library hands the level's polygon scratch (device pointer, n_int32 32-bit
  * words, non-zero on exactly one rank per slot) to `fn`, which must sum it over all ranks in place
- * (e.g. ncclAllReduce / torch.distributed.all_reduce on an int32 view) and return 0 after the result
- * is visible on the device.  Frontier, visited set and mesh are replicated and bit-identical. */
-typedef int (*am_allreduce_fn)(void *user, void *device_ptr, int64_t n_int32);
+ * (e.g. ncclAllReduce / torch.distributed.all_reduce on an int32 view) ordered on `cuda_stream` (the
+ * engine's stream: no host synchronisation is needed on either side) and return 0.  Frontier, visited
+ * set and mesh are replicated and bit-identical. */
+typedef int (*am_allreduce_fn)(void *user, void *device_ptr, int64_t n_int32, void *cuda_stream);
 int am_set_shard(am_handle *h, int rank, int world, am_allreduce_fn fn, void *user);
 
 int am_get_stats(const am_handle *h, am_stats *out);

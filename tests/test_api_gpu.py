@@ -1,0 +1,76 @@
+"""GPU tests of the public API: AnalyticMarching() (reference backend/main.py:335-559), voxel mode, and the
+pybind11 `cuam` module with the reference's call sequence (backend/main.py:441-471)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.cases import build_case
+from analyticmesh_b200 import zoo
+from analyticmesh_b200.polymesh import PolyMesh, load_ply_header
+
+pytestmark = pytest.mark.gpu
+
+
+def test_analytic_marching_api_chair(tmp_path):
+    from analyticmesh_b200 import AnalyticMarching
+    ply = str(tmp_path / "chair.ply")
+    cfg = {'method': 'dichotomy', 'args': {'init_num': 512, 'try_pts_num': 4096, 'init_ball_radius': 1.0,
+                                           'iter_max': 100, 'avg_eps': 1e-3, 'time_out': 60,
+                                           'provided_surfpts': None, 'provided_surfstd': None}}
+    ret = AnalyticMarching(zoo.chair(), ply, init_configs=cfg, seed=0)
+    assert {'init_point_time', 'init_cuda_time', 'am_time', 'export_time'} <= set(ret)
+    assert 'w_extra_constraints' not in cfg['args']            # the caller's dict is not mutated (App. B-14)
+    head = load_ply_header(ply)
+    assert head['face_num'] == 248228 and head['vertex_num'] == 248228      # SURVEY App. D known answer
+    # second call re-uses the environment (reference main.py:437-449)
+    ret2 = AnalyticMarching(zoo.chair(), ply, init_configs=cfg, seed=1, save_polymesh=False, scale=2.0,
+                            center=[1.0, 0.0, 0.0])
+    assert ret2['init_cuda_time'] == 0.0
+    m = PolyMesh(ply)
+    assert not m.is_polymesh() and m.num_polyfaces() == 2 * 248228
+    v = np.asarray(m.vertices())
+    assert v[:, 0].mean() > 0.9                                 # scaled and translated
+
+
+def test_voxel_mode_covers_the_surface(tmp_path):
+    from analyticmesh_b200 import AnalyticMarching
+    ply = str(tmp_path / "vox.ply")
+    ret = AnalyticMarching(zoo.chair(), ply, voxel_configs={'voxel_size': 0.5}, seed=0)
+    assert ret['am_time'] > 0
+    m = PolyMesh(ply)
+    assert m.num_polyfaces() >= 248228                          # faces cut by voxel walls are split
+    v = np.asarray(m.vertices(), dtype=np.float64)
+    info = build_case("chair")["info"]
+    assert np.abs(info.forward(v)[0]).max() < 1e-5              # float32 vertices on the surface
+
+
+def test_pybind_module_matches_ctypes_binding(tmp_path):
+    """the reference's five-call sequence through analyticmesh_b200/build/cuam*.so with torch CUDA tensors"""
+    from analyticmesh_b200.build import cuam as pyb
+    from tests import parity
+    case = build_case("chair_cube")
+    info = case["info"]
+    dev = torch.device("cuda")
+    t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev).contiguous()  # noqa: E731
+    pyb.Init(float_type="float64", nodesnum=info.nodes, arc_table=torch.from_numpy(info.arc_table),
+             num_extra_constraints=len(case["b_extra"]))
+    pyb.AnalyticMarching(weights=[t(w) for w in info.weights], biases=[t(b) for b in info.biases],
+                         states=torch.from_numpy(case["states"]).to(dev), points=t(case["points"]), arc_tm=[],
+                         w_extra_constraints=t(case["w_extra"]).reshape(-1, 3), b_extra_constraints=t(case["b_extra"]),
+                         iso=0.0, flip_insideout=False)
+    pyb.CombineMesh(scale=1.0, center=[0.0, 0.0, 0.0])
+    a = str(tmp_path / "a.ply")
+    pyb.ExportMesh(file_path=a, is_polymesh=True, is_float32=False)
+    st = pyb.Stats()
+    pyb.Destroy()
+    from analyticmesh_b200 import cuam
+    parity.run_engine(case)
+    b = str(tmp_path / "b.ply")
+    cuam.ExportMesh(file_path=b, is_polymesh=True, is_float32=False)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert st["n_faces"] == 685
+    with pytest.raises(RuntimeError):
+        pyb.Init(float_type="float64", nodesnum=[2, 5, 1], arc_table=torch.zeros(1, 1, dtype=torch.int32),
+                 num_extra_constraints=0)
