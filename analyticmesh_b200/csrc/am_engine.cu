@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/am_b200.h"
 #include "clip.cuh"
 #include "common.cuh"
@@ -42,15 +44,107 @@ struct CudaFail {
                            std::to_string(__LINE__) + ")"};                                               \
     } while (0)
 
+// ---- virtual-memory backed growth (CUDA VMM through the runtime's driver entry points: no libcuda link)
+struct VmApi {
+    bool ok = false;
+    size_t gran = 0;
+    int device = 0;
+    decltype(&cuMemAddressReserve) reserve = nullptr;
+    decltype(&cuMemAddressFree) free_va = nullptr;
+    decltype(&cuMemCreate) create = nullptr;
+    decltype(&cuMemRelease) release = nullptr;
+    decltype(&cuMemMap) map = nullptr;
+    decltype(&cuMemUnmap) unmap = nullptr;
+    decltype(&cuMemSetAccess) set_access = nullptr;
+    decltype(&cuMemGetAllocationGranularity) granularity = nullptr;
+    CUmemAllocationProp prop{};
+    size_t va_span = 0;          // virtual range reserved per buffer
+
+    static VmApi &get()
+    {
+        static VmApi api = [] {
+            VmApi a;
+            if (const char *e = getenv("AM_B200_NO_VMM")) if (atoi(e)) return a;
+            auto sym = [](const char *name, void **fn) {
+                cudaDriverEntryPointQueryResult q;
+                return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess &&
+                       q == cudaDriverEntryPointSuccess && *fn != nullptr;
+            };
+            if (!sym("cuMemAddressReserve", (void **)&a.reserve) || !sym("cuMemAddressFree", (void **)&a.free_va) ||
+                !sym("cuMemCreate", (void **)&a.create) || !sym("cuMemRelease", (void **)&a.release) ||
+                !sym("cuMemMap", (void **)&a.map) || !sym("cuMemUnmap", (void **)&a.unmap) ||
+                !sym("cuMemSetAccess", (void **)&a.set_access) ||
+                !sym("cuMemGetAllocationGranularity", (void **)&a.granularity)) {
+                cudaGetLastError();
+                return a;
+            }
+            if (cudaGetDevice(&a.device) != cudaSuccess) return a;
+            a.prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+            a.prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+            a.prop.location.id = a.device;
+            if (a.granularity(&a.gran, &a.prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || a.gran == 0)
+                return a;
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return a;
+            a.va_span = (total_b + a.gran - 1) / a.gran * a.gran;
+            a.ok = true;
+            return a;
+        }();
+        return api;
+    }
+};
+
+// Device buffer that grows.  With `vm` set (the big append-only arenas) growth maps more physical memory
+// behind a reserved virtual range: the pointer never moves, nothing is copied or freed, and no device
+// synchronisation is needed.  Otherwise (or if VMM is unavailable) classic malloc + copy + free.
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool vm = false;
+    std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
     template <typename T>
     T *as() const { return static_cast<T *>(p); }
+
+    bool grow_vm(size_t bytes)
+    {
+        VmApi &api = VmApi::get();
+        if (!api.ok) return false;
+        if (!p) {
+            CUdeviceptr va = 0;
+            if (api.reserve(&va, api.va_span, 0, 0, 0) != CUDA_SUCCESS) return false;
+            p = reinterpret_cast<void *>(va);
+        }
+        if (bytes > api.va_span) return false;
+        size_t add = std::max(bytes - cap, std::max(cap / 2, size_t(32) << 20));
+        add = (add + api.gran - 1) / api.gran * api.gran;
+        if (cap + add > api.va_span) add = api.va_span - cap;
+        CUmemGenericAllocationHandle hnd;
+        if (api.create(&hnd, add, &api.prop, 0) != CUDA_SUCCESS) {          // retry with the bare minimum
+            add = (bytes - cap + api.gran - 1) / api.gran * api.gran;
+            if (api.create(&hnd, add, &api.prop, 0) != CUDA_SUCCESS) throw CudaFail{"out of device memory (cuMemCreate)"};
+        }
+        const CUdeviceptr at = reinterpret_cast<CUdeviceptr>(p) + cap;
+        if (api.map(at, add, 0, hnd, 0) != CUDA_SUCCESS) {
+            api.release(hnd);
+            throw CudaFail{"cuMemMap failed"};
+        }
+        CUmemAccessDesc acc{};
+        acc.location = api.prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (api.set_access(at, add, &acc, 1) != CUDA_SUCCESS) throw CudaFail{"cuMemSetAccess failed"};
+        chunks.emplace_back(hnd, add);
+        cap += add;
+        return true;
+    }
+
     // grow to at least `bytes`; keeps the first `keep` bytes
     void reserve(size_t bytes, size_t keep = 0, bool geometric = true)
     {
         if (bytes <= cap) return;
+        if (vm && (p == nullptr || !chunks.empty())) {
+            if (grow_vm(bytes)) return;
+            if (!chunks.empty()) throw CudaFail{"virtual range exhausted"};
+        }
         size_t want = bytes;
         if (geometric && cap) want = std::max(bytes, cap * 2);
         void *np = nullptr;
@@ -63,7 +157,20 @@ struct DevBuf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (!chunks.empty() || (vm && p && VmApi::get().ok && cap == 0)) {
+            VmApi &api = VmApi::get();
+            cudaDeviceSynchronize();
+            size_t off = 0;
+            for (auto &c : chunks) {
+                api.unmap(reinterpret_cast<CUdeviceptr>(p) + off, c.second);
+                api.release(c.first);
+                off += c.second;
+            }
+            chunks.clear();
+            if (p) api.free_va(reinterpret_cast<CUdeviceptr>(p), api.va_span);
+        } else if (p) {
+            cudaFree(p);
+        }
         p = nullptr;
         cap = 0;
     }
@@ -208,13 +315,13 @@ struct am_handle {
     void ensure_states(size_t want)
     {
         if (want <= cap_states) return;
-        size_t ncap = std::max<size_t>(want, std::max<size_t>(cap_states * 2, 1 << 14));
+        size_t ncap = std::max<size_t>(want, std::max<size_t>(cap_states + cap_states / 2, 1 << 16));
         const size_t keep = (size_t)n_states;
         keys.reserve(ncap * kw * 4, keep * kw * 4, false);
         hsum.reserve(ncap * 8, keep * 8, false);
         parent.reserve(ncap * 4, keep * 4, false);
         via.reserve(ncap * 4, keep * 4, false);
-        seedpt.reserve(ncap * 24, keep * 24, false);
+        seedpt.reserve(ncap * 32, keep * 32, false);
         face_off.reserve((ncap + 1) * 8, (keep + 1) * 8, false);
         owner.reserve(ncap, keep, false);
         cap_states = ncap;
@@ -222,14 +329,14 @@ struct am_handle {
     void ensure_corners(size_t want, size_t keep)
     {
         if (want <= cap_corners) return;
-        size_t ncap = std::max<size_t>(want, std::max<size_t>(cap_corners * 2, 1 << 16));
+        size_t ncap = std::max<size_t>(want, std::max<size_t>(cap_corners + cap_corners / 2, 1 << 18));
         face_edges.reserve(ncap * 4, keep * 4, false);
         face_xyz.reserve(ncap * 24, keep * 24, false);
         cap_corners = ncap;
     }
     void ensure_table(size_t entries)
     {
-        uint32_t want = 1u << 12;
+        uint32_t want = 1u << 16;
         while ((size_t)want < entries * 2) want <<= 1;
         if (want <= tcap) return;
         table.reserve((size_t)want * 8, 0, false);
@@ -620,7 +727,7 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     ca.equ = h->equ.as<double>();
     ca.extra = h->extra.as<double>();
     ca.L = h->L; ca.E = h->E; ca.S = n; ca.flip = flip;
-    ca.seedpt = h->seedpt.as<double>() + (size_t)sid0 * 3;
+    ca.seedpt = h->seedpt.as<double>() + (size_t)sid0 * 4;
     ca.idx = idx;
     ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
     ca.counters = h->counters.as<unsigned long long>();
@@ -890,6 +997,10 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
                 h->n_tm = std::max(h->n_tm, sk.tm + 1);
             }
         }
+        for (DevBuf *b : {&h->keys, &h->hsum, &h->parent, &h->via, &h->seedpt, &h->face_off, &h->owner, &h->face_edges,
+                          &h->face_xyz, &h->lvl_planes[0], &h->lvl_planes[1], &h->xchg, &h->cand_slot, &h->f_verts,
+                          &h->planes, &h->table})
+            b->vm = true;
         h->Wt.resize(h->D + 1); h->bias.resize(h->D + 1);
         h->Mpad.assign(h->D + 1, 0); h->Kpad.assign(h->D + 1, 0);
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));

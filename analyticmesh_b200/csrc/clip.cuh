@@ -38,7 +38,7 @@ struct ClipArgs {
     const double *equ;        // [S][4]
     const double *extra;      // [E][4]
     int L, E, S, flip;
-    const double *seedpt;     // [S][3] seed point of state 0 of the chunk
+    const double *seedpt;     // [S][4] seed point (x, y, z) and size hint (0 = none) of state 0 of the chunk
     const int *idx;           // optional list of the states to process (sharded mode); S = its length
     int *out_cnt;             // [S]
     int *out_edges;           // [S][VSLOTS]
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
 {
     extern __shared__ __align__(16) double s_ring[];  // [warp][CLIP_DEPTH][32 lanes][4]: plane rows in flight
     __shared__ double s_pl[CLIP_WARPS][VSLOTS][4];   // plane of every polygon edge
-    __shared__ double s_vx[CLIP_WARPS][VSLOTS][3];   // vertex j = edge j  ^  edge j+1
+    __shared__ __align__(16) double s_vx[CLIP_WARPS][VSLOTS + 4][4];   // vertex j = edge j ^ edge j+1 (x, y, z, -);
+                                                     // slots k..k+3 repeat vertex 0 (unguarded 4-way loop)
     __shared__ int s_ed[CLIP_WARPS][VSLOTS];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
     if (slot >= a.S) return;
     const int s = a.idx ? a.idx[slot] : slot;
     double(*pl)[4] = s_pl[wib];
-    double(*vx)[3] = s_vx[wib];
+    double(*vx)[4] = s_vx[wib];
     int *ed = s_ed[wib];
     const unsigned FULL = 0xFFFFFFFFu;
 
@@ -95,23 +96,32 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
 #pragma unroll
     for (int j = 0; j < 4; ++j) eq[j] = a.equ[(size_t)s * 4 + j];
     const double nn = eq[0] * eq[0] + eq[1] * eq[1] + eq[2] * eq[2];
+    const bool dead = !(nn > 0.0) || !isfinite(nn) || !isfinite(eq[3]);
+    const double sp[3] = {a.seedpt[(size_t)s * 4 + 0], a.seedpt[(size_t)s * 4 + 1], a.seedpt[(size_t)s * 4 + 2]};
+    const double hint = a.seedpt[(size_t)s * 4 + 3];
+    const double huge = 1e4 * fmax(1.0, fmax(fabs(sp[0]), fmax(fabs(sp[1]), fabs(sp[2]))));
+    // The starting square is a few times the parent polygon's extent (children resemble their parents),
+    // so only the planes near the face ever cut it.  If an artificial edge survives, the square was too
+    // small: retry 64x larger, at the latest with the huge default on the third attempt.
+    double big = (hint > 0.0 && isfinite(hint)) ? fmin(8.0 * hint, huge) : huge;
     int k = 0;
-    bool dead = !(nn > 0.0) || !isfinite(nn) || !isfinite(eq[3]);
-
+    int n_inconsistent = 0;
+    bool overflow = false;
+    const int C = a.L + a.E;
+    for (int attempt = 0;; ++attempt) {
+    k = 0;
+    overflow = false;
     if (!dead) {
         // centre of the bounding square: seed point projected onto the level plane
-        const double sp[3] = {a.seedpt[(size_t)s * 3 + 0], a.seedpt[(size_t)s * 3 + 1], a.seedpt[(size_t)s * 3 + 2]};
         const double t = (eq[0] * sp[0] + eq[1] * sp[1] + eq[2] * sp[2] + eq[3]) / nn;
         const double x0[3] = {sp[0] - t * eq[0], sp[1] - t * eq[1], sp[2] - t * eq[2]};
-        const double big = 1e4 * fmax(1.0, fmax(fabs(sp[0]), fmax(fabs(sp[1]), fabs(sp[2]))));
         // in-plane orthonormal basis (u, v) with u x v along +n
         const double inv = rsqrt(nn);
         const double n[3] = {eq[0] * inv, eq[1] * inv, eq[2] * inv};
         int ax = 0;
         if (fabs(n[1]) < fabs(n[ax])) ax = 1;
         if (fabs(n[2]) < fabs(n[ax])) ax = 2;
-        double e[3] = {0, 0, 0};
-        e[ax] = 1.0;
+        const double e[3] = {ax == 0 ? 1.0 : 0.0, ax == 1 ? 1.0 : 0.0, ax == 2 ? 1.0 : 0.0};
         double u[3] = {n[1] * e[2] - n[2] * e[1], n[2] * e[0] - n[0] * e[2], n[0] * e[1] - n[1] * e[0]};
         const double ul = rsqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
         u[0] *= ul; u[1] *= ul; u[2] *= ul;
@@ -133,10 +143,11 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
         k = 4;
     }
     __syncwarp();
+    if (lane < 4) {   // padding slots
+        vx[k + lane][0] = vx[0][0]; vx[k + lane][1] = vx[0][1]; vx[k + lane][2] = vx[0][2];
+    }
+    __syncwarp();
 
-    const int C = a.L + a.E;
-    int n_inconsistent = 0;
-    bool overflow = false;
     // row of constraint c for this state (layer 1 rows are shared, extra constraints follow the neurons)
     auto row_of = [&](int c) -> const double * {
         return (c < a.n1) ? a.P1 + (size_t)c * 4
@@ -170,27 +181,30 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
         double rs = 0.0;
         bool cuts = false;
         if (c < C) {
-            double sg = 1.0;
-            if (c < a.L && ((key[c >> 5] >> (c & 31)) & 1u)) sg = -1.0;
-            p[0] = sg * lo.x; p[1] = sg * lo.y; p[2] = sg * hi.x; p[3] = sg * hi.y;
-            // any_j (d_j * rs > EPS)  <=>  (max_j d_j) * rs > EPS  because rs >= 0 and the product is
-            // monotone; rs (a double rsqrt) is only needed when some vertex is on the positive side
-            double dmax = -INFINITY;
-            bool nan_seen = false;
-            for (int j = 0; j < k; ++j) {
-                const double d = p[0] * vx[j][0] + p[1] * vx[j][1] + p[2] * vx[j][2] + p[3];
-                dmax = fmax(dmax, d);
-                nan_seen |= (d != d);
+            // sign 1 - 2 bit applied as an XOR on the IEEE sign bit (exact, and off the FP64 pipe)
+            const int flipbit = (c < a.L) ? int((key[c >> 5] >> (c & 31)) & 1u) << 31 : 0;
+            p[0] = __hiloint2double(__double2hiint(lo.x) ^ flipbit, __double2loint(lo.x));
+            p[1] = __hiloint2double(__double2hiint(lo.y) ^ flipbit, __double2loint(lo.y));
+            p[2] = __hiloint2double(__double2hiint(hi.x) ^ flipbit, __double2loint(hi.x));
+            p[3] = __hiloint2double(__double2hiint(hi.y) ^ flipbit, __double2loint(hi.y));
+            // Fast filter: d_j * rs > EPS needs d_j > 0 (rs >= 0; NaN compares false either way), so a
+            // plane with no vertex on its positive side cannot cut.  Slots k..k+3 repeat vertex 0, so the
+            // loop runs unguarded in steps of four.
+            bool pos = false;
+            for (int j = 0; j < k; j += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double2 xy = *reinterpret_cast<const double2 *>(&vx[j + u][0]);
+                    const double z = vx[j + u][2];
+                    const double d = p[0] * xy.x + p[1] * xy.y + p[2] * z + p[3];
+                    pos |= (d > 0.0);
+                }
             }
-            if (dmax > 0.0 || nan_seen) {
+            if (pos) {   // rare: evaluate the reference's predicate exactly
                 rs = rsqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-                if (nan_seen) {   // keep the reference's NaN semantics exactly: test every vertex
-                    for (int j = 0; j < k; ++j) {
-                        const double d = p[0] * vx[j][0] + p[1] * vx[j][1] + p[2] * vx[j][2] + p[3];
-                        cuts |= (d * rs > EPS_FEAS);
-                    }
-                } else {
-                    cuts = (dmax * rs > EPS_FEAS);
+                for (int j = 0; j < k; ++j) {
+                    const double d = p[0] * vx[j][0] + p[1] * vx[j][1] + p[2] * vx[j][2] + p[3];
+                    cuts |= (d * rs > EPS_FEAS);
                 }
             }
         }
@@ -253,10 +267,20 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
             }
             __syncwarp();
             k = knew;
+            if (lane < 4) {   // refresh the padding slots
+                vx[k + lane][0] = vx[0][0]; vx[k + lane][1] = vx[0][1]; vx[k + lane][2] = vx[0][2];
+            }
+            __syncwarp();
         }
     }
 
     asm volatile("cp.async.wait_all;\n" ::);   // the loop may leave early with copies still in flight
+    // artificial edge left and the square was not yet the huge default -> too small a start: retry
+    const bool art_left = (k > 0) && !overflow && __any_sync(FULL, (lane < k) && (ed[lane] < 0));
+    if (!art_left || big >= huge) break;
+    big = (attempt >= 1) ? huge : fmin(big * 64.0, huge);
+    __syncwarp();
+    }   // attempts
 
     // ---- finish: validity, orientation, canonical rotation --------------------------------------
     int unbounded = 0;

@@ -213,9 +213,18 @@ __global__ void finalize_kernel(const LevelArgs a)
             if (a.owner) a.owner[nid] = a.owner[sid];
             const int j2 = (j + 1 == k) ? 0 : j + 1;
             const double *p = a.face_xyz + (size_t)(fo + j) * 3, *q2 = a.face_xyz + (size_t)(fo + j2) * 3;
-            a.seedpt[(size_t)nid * 3 + 0] = 0.5 * (p[0] + q2[0]);
-            a.seedpt[(size_t)nid * 3 + 1] = 0.5 * (p[1] + q2[1]);
-            a.seedpt[(size_t)nid * 3 + 2] = 0.5 * (p[2] + q2[2]);
+            const double mx = 0.5 * (p[0] + q2[0]), my = 0.5 * (p[1] + q2[1]), mz = 0.5 * (p[2] + q2[2]);
+            // extent of the parent's polygon around the shared edge: a hint for the size of the child's
+            // polygon (clip.cuh starts from a square of a few times this size and retries if it was too small)
+            double ext = 0.0;
+            for (int c = 0; c < k; ++c) {
+                const double *v = a.face_xyz + (size_t)(fo + c) * 3;
+                ext = fmax(ext, fmax(fabs(v[0] - mx), fmax(fabs(v[1] - my), fabs(v[2] - mz))));
+            }
+            a.seedpt[(size_t)nid * 4 + 0] = mx;
+            a.seedpt[(size_t)nid * 4 + 1] = my;
+            a.seedpt[(size_t)nid * 4 + 2] = mz;
+            a.seedpt[(size_t)nid * 4 + 3] = ext;
             a.table.slots[slot] = (v & 0xFFFFFFFF00000000ull) | uint32_t(nid);
         }
         ++nid;
@@ -304,9 +313,10 @@ __global__ void x_finalize_kernel(const XArgs a)
         a.hsum_w[nid] = a.xh[i];
         a.parent[nid] = a.xparent ? a.xparent[i] : -1;
         a.via_edge[nid] = a.xvia ? a.xvia[i] : -1;
-        a.seedpt[(size_t)nid * 3 + 0] = a.xpt[(size_t)i * 3 + 0];
-        a.seedpt[(size_t)nid * 3 + 1] = a.xpt[(size_t)i * 3 + 1];
-        a.seedpt[(size_t)nid * 3 + 2] = a.xpt[(size_t)i * 3 + 2];
+        a.seedpt[(size_t)nid * 4 + 0] = a.xpt[(size_t)i * 3 + 0];
+        a.seedpt[(size_t)nid * 4 + 1] = a.xpt[(size_t)i * 3 + 1];
+        a.seedpt[(size_t)nid * 4 + 2] = a.xpt[(size_t)i * 3 + 2];
+        a.seedpt[(size_t)nid * 4 + 3] = 0.0;                  // no size hint for a seed state
         const int slot = a.x_slot[i];
         a.table.slots[slot] = (a.table.slots[slot] & 0xFFFFFFFF00000000ull) | uint32_t(nid);
     }
