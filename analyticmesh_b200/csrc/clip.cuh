@@ -92,6 +92,11 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
     const unsigned FULL = 0xFFFFFFFFu;
 
     const uint32_t *key = a.keys + (size_t)s * a.kw;
+    // the key lives in registers: lane l holds words l, l+32, l+64, l+96 (L <= 4096); the word of a
+    // 32-row block is fetched with one shuffle instead of a dependent global load per iteration
+    const int kwords = (a.L + 31) >> 5;
+    uint32_t kreg0 = (lane < kwords) ? key[lane] : 0u, kreg1 = (lane + 32 < kwords) ? key[lane + 32] : 0u;
+    uint32_t kreg2 = (lane + 64 < kwords) ? key[lane + 64] : 0u, kreg3 = (lane + 96 < kwords) ? key[lane + 96] : 0u;
     double eq[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) eq[j] = a.equ[(size_t)s * 4 + j];
@@ -177,12 +182,19 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
         const double2 lo = *reinterpret_cast<const double2 *>(mine);
         const double2 hi = *reinterpret_cast<const double2 *>(mine + 2);
         fetch(blk + CLIP_DEPTH - 1);
+        uint32_t kword;   // activation bits of rows base .. base+31 (warp-uniform source lane)
+        if (blk < 128) {
+            const uint32_t sel = (blk < 32) ? kreg0 : (blk < 64) ? kreg1 : (blk < 96) ? kreg2 : kreg3;
+            kword = __shfl_sync(FULL, sel, blk & 31);
+        } else {
+            kword = (blk < kwords) ? key[blk] : 0u;
+        }
         double p[4] = {0, 0, 0, 0};
         double rs = 0.0;
         bool cuts = false;
         if (c < C) {
             // sign 1 - 2 bit applied as an XOR on the IEEE sign bit (exact, and off the FP64 pipe)
-            const int flipbit = (c < a.L) ? int((key[c >> 5] >> (c & 31)) & 1u) << 31 : 0;
+            const int flipbit = (c < a.L) ? int((kword >> lane) & 1u) << 31 : 0;
             p[0] = __hiloint2double(__double2hiint(lo.x) ^ flipbit, __double2loint(lo.x));
             p[1] = __hiloint2double(__double2hiint(lo.y) ^ flipbit, __double2loint(lo.y));
             p[2] = __hiloint2double(__double2hiint(hi.x) ^ flipbit, __double2loint(hi.x));

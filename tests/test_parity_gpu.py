@@ -182,3 +182,68 @@ def test_engine_against_reference_golden(fname):
     # |f(v)| no worse than the reference's own residual (north_star)
     v, _, _ = eng["mesh"]
     assert np.abs(case["info"].forward(v)[0]).max() <= max(g["max_abs_f"], 1e-12) * 1.0 + 1e-12
+
+
+# ---------------------------------------------------------------- edge cases --------------------
+def test_iso_offset_matches_oracle(oracle_lib):
+    case = build_case("skipnet")
+    eng = parity.run_engine(case, iso=0.03)
+    orc = oracle_lib.march(case["info"], case["states"], case["points"], None, None, 0.03)
+    rep = parity.compare_with_oracle(eng, orc, case["info"].state_len)
+    # seeds were bisected for iso = 0: some seed regions miss the 0.03 level set, so compare FACES
+    assert rep["face_keys_equal"] and rep["loops_equal"] and rep["max_vertex_err"] < 1e-9, rep
+    v, _, _ = eng["mesh"]
+    assert np.abs(case["info"].forward(v)[0] - 0.03).max() < 1e-9
+
+
+def test_float32_environment_accepts_float32_buffers(oracle_lib):
+    """Init('float32') takes float32 tensors like the reference; this engine computes in float64
+    (a superset of the precision), so the result equals the float64 run on the same weights."""
+    case = build_case("chair_cube")      # chair.onnx weights are float32 values
+    a = parity.engine_faces(parity.run_engine(case, float_type="float32", combine=False), case["info"].state_len)
+    b = parity.engine_faces(parity.run_engine(case, float_type="float64", combine=False), case["info"].state_len)
+    # the seed points are rounded to float32 on the way in: same regions, same loops
+    assert set(k for k, v in a.items() if v is not None) == set(k for k, v in b.items() if v is not None)
+    for k, v in a.items():
+        if v is not None:
+            assert v[0] == b[k][0]
+
+
+def test_duplicate_single_and_faceless_seeds(oracle_lib):
+    case = build_case("chair")
+    info = case["info"]
+    # (a) one seed only: the whole connected surface is still found
+    one = dict(case, states=case["states"][:1], points=case["points"][:1])
+    eng = parity.run_engine(one, combine=False)
+    assert eng["stats"]["n_faces"] == 248228 and eng["stats"]["n_unique_seeds"] == 1
+    # (b) duplicates collapse; a seed far from the surface has a region without a face and spawns nothing
+    far = np.array([[5.0, 5.0, 5.0]])
+    _, far_state = info.forward(far)
+    small = build_case("chair_cube")
+    mixed = dict(small, states=np.concatenate([small["states"], small["states"], far_state]),
+                 points=np.concatenate([small["points"], small["points"], far]))
+    eng = parity.run_engine(mixed, combine=False)
+    orc = oracle_lib.march(info, mixed["states"], mixed["points"], mixed["w_extra"], mixed["b_extra"])
+    rep = parity.compare_with_oracle(eng, orc, info.state_len)
+    assert rep["keys_equal"] and rep["loops_equal"], rep
+    assert eng["stats"]["n_seeds"] == 2 * len(small["states"]) + 1
+    assert eng["stats"]["n_faces"] == 685
+
+
+def test_environment_switches_between_networks(oracle_lib):
+    for name in ("skipnet", "chair_cube", "polytope", "skipnet"):
+        case = build_case(name)
+        eng = parity.run_engine(case, combine=False)
+        orc = oracle_lib.march(case["info"], case["states"], case["points"], case["w_extra"], case["b_extra"])
+        assert parity.compare_with_oracle(eng, orc, case["info"].state_len)["keys_equal"], name
+
+
+def test_fallback_without_resident_planes_is_identical(monkeypatch):
+    """AM_B200_INCREMENTAL=0 forces chunked full recomputation: same bytes out."""
+    case = build_case("mlp4x128s")
+    a = parity.run_engine(case, combine=False)
+    monkeypatch.setenv("AM_B200_INCREMENTAL", "0")
+    b = parity.run_engine(case, combine=False)
+    assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["edges"], b["edges"])
+    assert np.array_equal(a["xyz"], b["xyz"])
+    assert b["stats"]["compose_flops"] > 1.5 * a["stats"]["compose_flops"]
