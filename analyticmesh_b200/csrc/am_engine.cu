@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <cuda.h>
+#include <dlfcn.h>
 
 #include "../../include/am_b200.h"
 #include "clip.cuh"
@@ -176,6 +177,37 @@ struct DevBuf {
     }
 };
 
+// ---- NCCL, bound at run time (the library is already loaded in a torch process; no link dependency)
+struct NcclApi {
+    struct UniqueId { char internal[128]; };
+    typedef int (*get_id_t)(UniqueId *);
+    typedef int (*init_rank_t)(void **comm, int nranks, UniqueId id, int rank);
+    typedef int (*allreduce_t)(const void *send, void *recv, size_t count, int dtype, int op, void *comm,
+                               cudaStream_t stream);
+    typedef int (*destroy_t)(void *comm);
+    get_id_t get_id = nullptr;
+    init_rank_t init_rank = nullptr;
+    allreduce_t allreduce = nullptr;
+    destroy_t destroy = nullptr;
+    bool ok = false;
+    static NcclApi &get()
+    {
+        static NcclApi api = [] {
+            NcclApi a;
+            void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) return a;
+            a.get_id = (get_id_t)dlsym(lib, "ncclGetUniqueId");
+            a.init_rank = (init_rank_t)dlsym(lib, "ncclCommInitRank");
+            a.allreduce = (allreduce_t)dlsym(lib, "ncclAllReduce");
+            a.destroy = (destroy_t)dlsym(lib, "ncclCommDestroy");
+            a.ok = a.get_id && a.init_rank && a.allreduce && a.destroy;
+            return a;
+        }();
+        return api;
+    }
+};
+
 struct Skip {
     int src;        // 0 = raw input, j >= 1 = hidden layer j
     int tm;         // transform index
@@ -236,6 +268,7 @@ struct am_handle {
     int shard_rank = 0, shard_world = 1;
     am_allreduce_fn shard_cb = nullptr;
     void *shard_user = nullptr;
+    void *nccl_comm = nullptr;                  // set by am_set_shard_nccl: collectives issued from C++
     DevBuf owner, xchg;
     long long shard_owned_states = 0;
     int *h_npre = nullptr;                      // pinned
@@ -521,6 +554,19 @@ struct am_handle {
         CK(cudaStreamSynchronize(stream));
     }
 
+    // in-place integer sum over all ranks, ordered on the engine's stream
+    void allreduce_i32(void *ptr, long long n32)
+    {
+        if (nccl_comm) {
+            const int rc = NcclApi::get().allreduce(ptr, ptr, (size_t)n32, /*ncclInt32*/ 2, /*ncclSum*/ 0, nccl_comm, stream);
+            if (rc != 0) throw CudaFail{"ncclAllReduce failed (" + std::to_string(rc) + ")"};
+        } else if (shard_cb) {
+            if (shard_cb(shard_user, ptr, n32, (void *)stream) != 0) throw CudaFail{"the host all-reduce callback failed"};
+        } else {
+            throw CudaFail{"sharded mode without a collective"};
+        }
+    }
+
     template <typename F>
     void dispatch_group(F &&f)
     {
@@ -701,17 +747,11 @@ void insert_seeds(am_handle *h, const uint8_t *states, const double *points, lon
     }
 }
 
-// per-level polygon scratch: separate buffers, or (sharded mode) three regions of one exchange buffer
+// per-level polygon scratch (stride VSLOTS per state)
 struct Scratch { int *cnt; int *edges; double *verts; };
 Scratch scratch_of(am_handle *h, size_t S)
 {
-    if (h->shard_world > 1) {
-        const size_t Sp = (S + 1) & ~size_t(1);
-        h->xchg.reserve(Sp * (4 + VSLOTS * 4 + VSLOTS * 24), 0, true);
-        char *b = h->xchg.as<char>();
-        return Scratch{reinterpret_cast<int *>(b), reinterpret_cast<int *>(b + Sp * 4),
-                       reinterpret_cast<double *>(b + Sp * 4 + Sp * VSLOTS * 4)};
-    }
+    (void)S;
     return Scratch{h->f_cnt.as<int>(), h->f_edges.as<int>(), h->f_verts.as<double>()};
 }
 
@@ -736,14 +776,33 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     CK(cudaGetLastError());
 }
 
-// scan + compact the polygons of the states [sid0, sid0+Sc) into the global CSR
+// scan + compact the polygons of the states [sid0, sid0+Sc) into the global CSR.
+// Sharded mode: the polygon sizes are summed over the ranks first (a rank's count is zero for states it
+// does not own), every rank then knows the level's CSR offsets, writes only its own polygons into the
+// zeroed CSR range, and the range is summed over the ranks: 4 + 28 B per corner cross NVLink instead of
+// the fixed-stride scratch.
 void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc)
 {
     cudaStream_t st = h->stream;
     unsigned long long *cnt = h->counters.as<unsigned long long>();
+    const bool sharded = h->shard_world > 1;
     h->f_off.reserve((size_t)Sc * 4, 0, false);
+    if (sharded) h->allreduce_i32(sc.cnt, Sc);
     h->scan(reinterpret_cast<uint32_t *>(sc.cnt), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
+    long long base = 0, n_lvl = 0;
+    if (sharded) {
+        CK(cudaMemcpyAsync(h->h_counters + CNT_CHUNK_CORNERS, cnt + CNT_CHUNK_CORNERS, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        base = (long long)h->h_counters[CNT_CORNERS];          // exact: read back at the end of the last level
+        n_lvl = (long long)h->h_counters[CNT_CHUNK_CORNERS];
+        if (n_lvl > 0) {
+            CK(cudaMemsetAsync(h->face_edges.as<int>() + base, 0, (size_t)n_lvl * 4, st));
+            CK(cudaMemsetAsync(h->face_xyz.as<double>() + base * 3, 0, (size_t)n_lvl * 24, st));
+        }
+    }
     CompactArgs co{};
+    co.owner = sharded ? h->owner.as<uint8_t>() : nullptr;
+    co.rank = h->shard_rank;
     co.cnt = sc.cnt; co.off = h->f_off.as<uint32_t>();
     co.edges = sc.edges; co.verts = sc.verts;
     co.S = Sc; co.sid0 = (int)sid0;
@@ -751,6 +810,10 @@ void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc)
     co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
     compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
     ++h->stats.n_launches;
+    if (sharded && n_lvl > 0) {
+        h->allreduce_i32(h->face_edges.as<int>() + base, n_lvl);
+        h->allreduce_i32(h->face_xyz.as<double>() + base * 3, n_lvl * 6);
+    }
     bump_counters_kernel<<<1, 32, 0, st>>>(cnt);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
@@ -824,7 +887,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
             have = true;
         }
         if (!have) CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 2) * 4, cudaMemcpyDeviceToHost, st));
-        if (sharded) CK(cudaMemsetAsync(h->xchg.p, 0, ((size_t)(S + 1) & ~size_t(1)) * (4 + VSLOTS * 4 + VSLOTS * 24), st));
+        if (sharded) CK(cudaMemsetAsync(sc.cnt, 0, (size_t)S * 4, st));   // counts of states owned elsewhere
         if (h->prev_resident) {
             copy_parent_rows_kernel<<<(unsigned)((S + 7) / 8), 256, 0, st>>>(
                 h->bucket.as<int>(), h->parent.as<int>(), (int)lb, (int)S, (int)h->prev_lb,
@@ -843,13 +906,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         if (timing) h->span_end(t0, 1);
         if (timing) t0 = h->span_begin();
         run_clip(h, lb, sharded ? n_mine : (int)S, base, flip, sharded ? h->perm.as<int>() : nullptr, sc);
-        if (sharded) {   // union of the ranks' polygons: every slot is non-zero on exactly one rank
-            const size_t Sp = ((size_t)S + 1) & ~size_t(1);
-            const long long n32 = (long long)(Sp * (4 + VSLOTS * 4 + VSLOTS * 24) / 4);
-            if (h->shard_cb(h->shard_user, h->xchg.p, n32, (void *)st) != 0)
-                throw CudaFail{"the host all-reduce callback failed"};
-        }
-        store_faces(h, lb, (int)S, sc);
+        store_faces(h, lb, (int)S, sc);   // sharded: + the level's collectives (sizes, edges, vertices)
         if (timing) h->span_end(t0, 2);
         h->prev_resident = true;
         h->prev_buf = cur;
@@ -1041,6 +1098,11 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
 void am_destroy(am_handle *h)
 {
     if (!h) return;
+    if (h->nccl_comm) {
+        cudaDeviceSynchronize();
+        NcclApi::get().destroy(h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
     h->free_all();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1057,6 +1119,45 @@ int am_set_shard(am_handle *h, int rank, int world, am_allreduce_fn fn, void *us
     h->shard_world = world;
     h->shard_cb = fn;
     h->shard_user = user;
+    return AM_OK;
+}
+
+int am_nccl_unique_id(void *out128)
+{
+    NcclApi &api = NcclApi::get();
+    if (!api.ok || !out128) return AM_ERR_STATE;
+    NcclApi::UniqueId id;
+    if (api.get_id(&id) != 0) return AM_ERR_CUDA;
+    memcpy(out128, id.internal, 128);
+    return AM_OK;
+}
+
+int am_set_shard_nccl(am_handle *h, int rank, int world, const void *unique_id128)
+{
+    if (!h) return AM_ERR_ARG;
+    NcclApi &api = NcclApi::get();
+    if (!api.ok) {
+        h->err = "am_set_shard_nccl: libnccl.so.2 could not be loaded";
+        return AM_ERR_STATE;
+    }
+    if (world < 2 || world > 255 || rank < 0 || rank >= world || !unique_id128) {
+        h->err = "am_set_shard_nccl: need 0 <= rank < world, 2 <= world <= 255 and a unique id";
+        return AM_ERR_ARG;
+    }
+    if (h->nccl_comm) {
+        api.destroy(h->nccl_comm);
+        h->nccl_comm = nullptr;
+    }
+    NcclApi::UniqueId id;
+    memcpy(id.internal, unique_id128, 128);
+    const int rc = api.init_rank(&h->nccl_comm, world, id, rank);
+    if (rc != 0) {
+        h->err = "am_set_shard_nccl: ncclCommInitRank failed (" + std::to_string(rc) + ")";
+        h->nccl_comm = nullptr;
+        return AM_ERR_CUDA;
+    }
+    h->shard_rank = rank;
+    h->shard_world = world;
     return AM_OK;
 }
 

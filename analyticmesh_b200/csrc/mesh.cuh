@@ -77,6 +77,8 @@ struct CompactArgs {
     int *face_edges;
     double *face_xyz;
     unsigned long long *counters; // CNT_CORNERS = running total before this chunk
+    const uint8_t *owner;         // sharded mode: only the owner's polygons are copied (others arrive by all-reduce)
+    int rank;
 };
 
 __global__ void compact_faces_kernel(const CompactArgs a)
@@ -91,7 +93,7 @@ __global__ void compact_faces_kernel(const CompactArgs a)
         if (s == a.S - 1) a.face_off[a.sid0 + s + 1] = base + k;
         if (k > 0) atomicAdd(a.counters + CNT_FACES, 1ull);
     }
-    if (lane < k) {
+    if (lane < k && (a.owner == nullptr || a.owner[a.sid0 + s] == a.rank)) {
         a.face_edges[base + lane] = a.edges[(size_t)s * VSLOTS + lane];
         const double *v = a.verts + ((size_t)s * VSLOTS + lane) * 3;
         double *o = a.face_xyz + (size_t)(base + lane) * 3;

@@ -37,7 +37,8 @@ class AmStats(ctypes.Structure):
 
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",
            "am_key_words", "am_state_len", "am_copy_states", "am_copy_faces", "am_copy_mesh", "am_load_weights",
-           "am_debug_planes", "am_compose_profile", "am_fp64_peak_tflops", "am_set_shard", "am_ply_parse_faces",
+           "am_debug_planes", "am_compose_profile", "am_fp64_peak_tflops", "am_set_shard", "am_nccl_unique_id",
+           "am_set_shard_nccl", "am_ply_parse_faces",
            "am_ply_pack_faces")
 
 
@@ -288,6 +289,19 @@ def set_shard(rank, world, allreduce):
     fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     _err(fn(_handle, int(rank), int(world), ctypes.cast(_shard_cb, ctypes.c_void_p) if _shard_cb else None, None),
          "set_shard")
+
+
+def set_shard_nccl(rank, world, broadcast_bytes):
+    """Spread ONE march over `world` processes with the per-level all-reduce issued by the library itself
+    (ncclAllReduce on the engine's stream).  `broadcast_bytes(b: bytes | None) -> bytes` must return rank 0's
+    128-byte NCCL unique id on every rank (analyticmesh_b200.parallel.broadcast_bytes)."""
+    buf = (ctypes.c_char * 128)()
+    if rank == 0:
+        _err(lib().am_nccl_unique_id(buf), "nccl_unique_id")
+    uid = broadcast_bytes(bytes(buf) if rank == 0 else None)
+    fn = lib().am_set_shard_nccl
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+    _err(fn(_handle, int(rank), int(world), uid), "set_shard_nccl")
 
 
 def fp64_peak_tflops():

@@ -48,3 +48,13 @@ def owner_of_seeds(n_seeds_unique, world):
     """Seed state i (after de-duplication, in id order) is owned by rank i % world; children inherit the
     owner of the parent that discovered them (csrc/frontier.cuh finalize_kernel)."""
     return np.arange(n_seeds_unique) % world
+
+
+def broadcast_bytes(payload, group=None, device=None):
+    """rank 0's `payload` (bytes, fixed length 128) on every rank, through torch.distributed."""
+    dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if payload is not None:
+        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(t, src=0, group=group)
+    return bytes(t.cpu().numpy().tobytes())

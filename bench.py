@@ -182,8 +182,8 @@ def main():
     torch.cuda.synchronize()
     init_cuda_time = time.time() - t0
     if world > 1:
-        from analyticmesh_b200.parallel import make_allreduce
-        cuam.set_shard(rank, world, make_allreduce(device=dev))
+        from analyticmesh_b200.parallel import broadcast_bytes
+        cuam.set_shard_nccl(rank, world, lambda b: broadcast_bytes(b, device=dev))
 
     def barrier():
         if world > 1:
@@ -216,6 +216,7 @@ def main():
         faces += last["n_faces"]
         launches += last["n_launches"]
         engine_s += last["seconds_march"]
+        phases = {k: last[k] for k in ("seconds_compose", "seconds_clip", "seconds_frontier")}
         p = cuam.compose_profile()
         gemm_ms += p["ms_total"]
         gemm_flops += p["flops"]
@@ -283,6 +284,7 @@ def main():
                                        "am_time": dt / args.steps, "am_plus_combine_host_buffers": e_dt / args.steps,
                                        "export_time": export_time, "ply_bytes": ply_bytes},
                        "engine_stream_seconds_per_step": engine_s / args.steps,
+                       "phase_seconds_last_step_rank0": phases,
                        "algorithmic_flops_per_face": fpf},
             "e2e": {"value": e_faces / e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

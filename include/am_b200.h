@@ -97,6 +97,11 @@ void am_destroy(am_handle *h);
  * set and mesh are replicated and bit-identical. */
 typedef int (*am_allreduce_fn)(void *user, void *device_ptr, int64_t n_int32, void *cuda_stream);
 int am_set_shard(am_handle *h, int rank, int world, am_allreduce_fn fn, void *user);
+/* Same, with the collective issued by the library itself: ncclAllReduce on the engine's stream
+ * (libnccl.so.2 is bound with dlopen).  Rank 0 calls am_nccl_unique_id, the host broadcasts the 128
+ * bytes (e.g. torch.distributed.broadcast), every rank calls am_set_shard_nccl (collective call). */
+int am_nccl_unique_id(void *out128);
+int am_set_shard_nccl(am_handle *h, int rank, int world, const void *unique_id128);
 
 int am_get_stats(const am_handle *h, am_stats *out);
 const char *am_last_error(const am_handle *h);   /* h may be NULL: error of the last failed am_create */

@@ -24,8 +24,11 @@ for name in (sys.argv[1:] or ["chair_cube", "skipnet", "chair", "mlp4x128s"]):
         info = case["info"]
         cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table,
                   num_extra_constraints=len(case["b_extra"]))
-        if shard:
+        if shard == 1:
             cuam.set_shard(rank, world, make_allreduce())
+        elif shard == 2:
+            from analyticmesh_b200.parallel import broadcast_bytes
+            cuam.set_shard_nccl(rank, world, broadcast_bytes)
         cuam.AnalyticMarching(weights=info.weights, biases=info.biases, states=case["states"], points=case["points"],
                               arc_tm=info.arc_tm, w_extra_constraints=case["w_extra"].reshape(-1, 3),
                               b_extra_constraints=case["b_extra"].reshape(-1), iso=0.0, flip_insideout=False)
@@ -39,9 +42,10 @@ for name in (sys.argv[1:] or ["chair_cube", "skipnet", "chair", "mlp4x128s"]):
             h.update(np.ascontiguousarray(a).tobytes())
         return h.hexdigest(), st
 
-    d1, s1 = digest(False)
-    d2, s2 = digest(True)
-    ok = d1 == d2
+    d1, s1 = digest(0)
+    d2, s2 = digest(2)
+    d3, s3 = digest(1)
+    ok = d1 == d2 == d3
     t = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
