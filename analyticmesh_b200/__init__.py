@@ -3,7 +3,7 @@ from .model import MLP
 from .onnx_io import save_model, load_model
 
 __all__ = ["MLP", "save_model", "load_model"]
-from .utils import get_boundary, estimate_am_time  # noqa: E402
+from .utils import get_boundary, estimate_am_time, simplify  # noqa: E402
 from .polymesh import PolyMesh, poly2tri, get_faces_num, load_ply_header  # noqa: E402
 
 
@@ -13,5 +13,5 @@ def AnalyticMarching(*args, **kwargs):
     return _am(*args, **kwargs)
 
 
-__all__ += ["AnalyticMarching", "get_boundary", "estimate_am_time", "PolyMesh", "poly2tri", "get_faces_num",
+__all__ += ["AnalyticMarching", "get_boundary", "estimate_am_time", "simplify", "PolyMesh", "poly2tri", "get_faces_num",
             "load_ply_header"]

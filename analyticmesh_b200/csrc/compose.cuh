@@ -73,6 +73,8 @@ struct GemmArgs {
     const int *perm;            // optional: tile slot i works on state perm[i] (states sorted by the layer
                                 // of their flipped neuron, see classify_kernel); nullptr = identity
     int m_tiles;                // Mpad / GM_BM; blockIdx.x = s_tile * m_tiles + m_tile
+    int tile_stride, tile_offset;   // this launch handles state tiles tile_offset, tile_offset + tile_stride, ...
+                                    // (independent chains of launches on several streams fill each other's tails)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) compose_gemm_kernel(const
 
     const int tid = threadIdx.x;
     const int m0 = (blockIdx.x % a.m_tiles) * GM_BM;      // m fastest: CTAs that share a B tile are co-resident
-    const int s0 = (blockIdx.x / a.m_tiles) * C::BS;
+    const int s0 = ((blockIdx.x / a.m_tiles) * a.tile_stride + a.tile_offset) * C::BS;
     const int S = a.S;
     const int KT = (a.K + C::BK - 1) / C::BK;
     const int lane = tid & 31, warp = tid >> 5;
@@ -234,12 +236,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) compose_gemm_kernel(const
 
 // from the raw input: P[s][m][0..2] += T[m][0..2]   (T == nullptr: += I3)   process.h:86-92,109-115
 __global__ void skip_input_kernel(double *out, long long out_stride, int M, int S, const double *T, const int *perm,
-                                  const int *n_active)
+                                  int tile_states, int tile_stride, int tile_offset)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (n_active) S = min(S, *n_active);
     if (t >= (long long)S * M) return;
     const int slot = int(t / M), m = int(t % M);
+    if ((slot / tile_states) % tile_stride != tile_offset) return;    // another chain's tile
     const int s = perm ? perm[slot] : slot;
     double *p = out + (size_t)s * out_stride + (size_t)m * 4;
     if (T != nullptr) {
@@ -254,14 +256,14 @@ __global__ void skip_input_kernel(double *out, long long out_stride, int M, int 
 // identity skip from hidden layer `src`: out[s][m][:] += bit(s, src_bit0+m) * in[s][m][:]   process.h:93-105
 __global__ void skip_hidden_identity_kernel(double *out, long long out_stride, const double *in, long long in_stride,
                                             const uint32_t *keys, int kw, int src_bit0, int M, int S, const int *perm,
-                                            const int *n_active)
+                                            int tile_states, int tile_stride, int tile_offset)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (n_active) S = min(S, *n_active);
     if (t >= (long long)S * M * 4) return;
     const int c = int(t & 3);
     const long long r = t >> 2;
     const int slot = int(r / M), m = int(r % M);
+    if ((slot / tile_states) % tile_stride != tile_offset) return;
     const int s = perm ? perm[slot] : slot;
     const int bit = src_bit0 + m;
     if ((keys[(size_t)s * kw + (bit >> 5)] >> (bit & 31)) & 1u)

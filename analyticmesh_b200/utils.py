@@ -21,3 +21,34 @@ def estimate_am_time(model):
     layers = len(nodes) - 2
     width = sum(nodes[1:-1]) / layers
     return (a * width) ** (b * layers + c) * width ** d * layers ** e * f
+
+
+def simplify(ply_path, save_ply_path=None, target_perc=0.01, meshlabserver_path="meshlabserver"):
+    """Pass-through to the external `meshlabserver` tool (quadric edge-collapse decimation to `target_perc`
+    of the faces, then removal of non-manifold edges and hole closing), like reference backend/utils.py:31-74.
+    The tool is not part of this package: a clear error is raised when it is not installed."""
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which(meshlabserver_path) is None:
+        raise RuntimeError(f"`{meshlabserver_path}` not found: simplify() only drives the external MeshLab server")
+    filters = (
+        '<!DOCTYPE FilterScript>\n<FilterScript>\n'
+        ' <filter name="Simplification: Quadric Edge Collapse Decimation">\n'
+        f'  <Param name="TargetPerc" value="{target_perc}" type="RichFloat"/>\n'
+        '  <Param name="QualityThr" value="0.5" type="RichFloat"/>\n'
+        '  <Param name="PreserveNormal" value="true" type="RichBool"/>\n'
+        '  <Param name="OptimalPlacement" value="true" type="RichBool"/>\n'
+        '  <Param name="PlanarQuadric" value="true" type="RichBool"/>\n'
+        '  <Param name="AutoClean" value="true" type="RichBool"/>\n'
+        ' </filter>\n'
+        ' <filter name="Select non Manifold Edges "/>\n <filter name="Delete Selected Faces"/>\n'
+        ' <filter name="Close Holes">\n  <Param name="MaxHoleSize" value="100" type="RichInt"/>\n </filter>\n'
+        '</FilterScript>\n')
+    out = ply_path if save_ply_path is None else save_ply_path
+    with tempfile.TemporaryDirectory() as tmp:
+        script = os.path.join(tmp, "script.mlx")
+        with open(script, "w") as f:
+            f.write(filters)
+        subprocess.run([meshlabserver_path, "-i", ply_path, "-o", out, "-s", script], check=True)
