@@ -26,6 +26,7 @@
 #include "compose.cuh"
 #include "frontier.cuh"
 #include "mesh.cuh"
+#include "split.cuh"
 
 using namespace amb;
 
@@ -208,6 +209,72 @@ struct NcclApi {
     }
 };
 
+// ---- tcgen05 split-integer composition (split.cuh): tensor maps + weight digits --------------------------
+struct TmaApi {
+    decltype(&cuTensorMapEncodeTiled) encode = nullptr;
+    static TmaApi &get()
+    {
+        static TmaApi api = [] {
+            TmaApi a;
+            cudaDriverEntryPointQueryResult q;
+            void *fn = nullptr;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                a.encode = (decltype(a.encode))fn;
+            else
+                cudaGetLastError();
+            return a;
+        }();
+        return api;
+    }
+};
+
+// 3-D map over int8 digit planes [SD][rows][pitch]: box = 32 K bytes x box_rows rows x SD planes, SWIZZLE_32B
+CUtensorMap make_digit_map(const void *ptr, int k_bytes, size_t pitch, size_t rows, int sd, int box_rows)
+{
+    TmaApi &api = TmaApi::get();
+    if (!api.encode) throw CudaFail{"cuTensorMapEncodeTiled is not available in this driver"};
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {(cuuint64_t)k_bytes, (cuuint64_t)rows, (cuuint64_t)sd};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * rows};
+    const cuuint32_t box[3] = {(cuuint32_t)SP_BK, (cuuint32_t)box_rows, (cuuint32_t)sd};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = api.encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw CudaFail{"cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")"};
+    return m;
+}
+
+// digits of a row-major (M, K) weight matrix, one power-of-two scale per row (see split.cuh)
+void split_weight_digits(const double *w, int M, int K, int Mpad, int Kpad, int sd, std::vector<signed char> &dig,
+                         std::vector<double> &scale)
+{
+    dig.assign((size_t)sd * Mpad * Kpad, 0);
+    scale.assign(Mpad, 0.0);
+    const int frac = 8 * sd - 2;
+    for (int m = 0; m < M; ++m) {
+        double mx = 0.0;
+        for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(w[(size_t)m * K + k]));
+        int e = 0;
+        if (mx > 0.0 && mx < 1.7e308) std::frexp(mx, &e);
+        const double mul = std::ldexp(1.0, frac - e);
+        scale[m] = std::ldexp(1.0, e - 6);
+        for (int k = 0; k < K; ++k) {
+            const unsigned long long Y = split_pack(std::llrint(w[(size_t)m * K + k] * mul), sd);
+            for (int t = 0; t < sd; ++t)
+                dig[((size_t)t * Mpad + m) * Kpad + k] = (signed char)((Y >> (8 * (sd - 1 - t))) & 0xFF);
+        }
+    }
+}
+
+struct SplitWeights {
+    DevBuf dig, scale;
+    CUtensorMap map;
+    int Kpad = 0, Mpad = 0;
+    bool ready = false;
+};
+
 struct Skip {
     int src;        // 0 = raw input, j >= 1 = hidden layer j
     int tm;         // transform index
@@ -264,7 +331,14 @@ struct am_handle {
     // sharded mode (one march over several GPUs): compose + clip of a state run on its owner rank only,
     // the per-level polygons are combined with an all-reduce supplied by the host (NCCL through
     // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
-    int gemm_variant = 0;
+    int gemm_variant = 0;                       // 0/1: FP64 DMMA tiles, 2: tcgen05 int8 split (split.cuh)
+    int split_digits = 7;
+    std::vector<SplitWeights> splitW, splitTM;  // index h = 1..D-1 / transform index
+    DevBuf bdig, bscale;                        // plane digits [SD][b_ncap][b_pitch] and column scales of the current launch
+    size_t b_ncap = 0, b_pitch = 0;
+    std::vector<std::pair<int, CUtensorMap>> b_maps;   // per K bytes; rebuilt when bdig moves
+    const void *b_maps_ptr = nullptr;
+    size_t b_maps_ncap = 0;
     static constexpr int MAX_CHAINS = 8;
     int n_chains = 0;   // 0 = automatic: 1 on a single GPU (launches fill the machine), 4 when sharded (measured +1.4 % at 8 GPUs)
     cudaStream_t chain_stream[MAX_CHAINS] = {};
@@ -323,6 +397,9 @@ struct am_handle {
         for (auto &b : bias) b.release();
         for (auto &b : TM) b.release();
         for (auto &b : TMt) b.release();
+        for (auto &w : splitW) { w.dig.release(); w.scale.release(); }
+        for (auto &w : splitTM) { w.dig.release(); w.scale.release(); }
+        bdig.release(); bscale.release();
         DevBuf *all[] = {&P1, &wout, &extra, &keys, &hsum, &parent, &via, &seedpt, &face_off, &face_edges, &face_xyz,
                          &table, &planes, &equ, &f_cnt, &f_off, &f_edges, &f_verts, &cand_slot, &nwin, &wbase, &scan_a,
                          &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates, &lvl_planes[0], &lvl_planes[1],
@@ -438,9 +515,58 @@ struct am_handle {
     }
 
     // ---------------- composition of one chunk: keys of states [sid0, sid0+Sc) -------------------
+    // ---- tcgen05 path: plane digits of the launch + tensor maps ------------------------------------------
+    CUtensorMap b_map(int kbytes)
+    {
+        if (b_maps_ptr != bdig.p || b_maps_ncap != b_ncap) {
+            b_maps.clear();
+            b_maps_ptr = bdig.p;
+            b_maps_ncap = b_ncap;
+        }
+        for (auto &kv : b_maps)
+            if (kv.first == kbytes) return kv.second;
+        b_maps.emplace_back(kbytes, make_digit_map(bdig.p, kbytes, b_pitch, b_ncap, split_digits, SP_BN));
+        return b_maps.back().second;
+    }
+    void ensure_split_scratch(size_t slots)
+    {
+        size_t pitch = SP_KPAD;
+        for (int l = 1; l <= D; ++l) pitch = std::max<size_t>(pitch, (size_t)(n[l] + SP_KPAD - 1) / SP_KPAD * SP_KPAD);
+        size_t ncap = (std::max<size_t>(slots, SP_BS) * 4 + SP_BN - 1) / SP_BN * SP_BN;
+        if (ncap <= b_ncap && pitch == b_pitch) return;
+        ncap = std::max(ncap, (b_ncap + b_ncap / 2 + SP_BN - 1) / SP_BN * SP_BN);
+        bdig.reserve((size_t)split_digits * ncap * pitch, 0, false);
+        bscale.reserve(ncap * 8, 0, false);
+        b_ncap = ncap;
+        b_pitch = pitch;
+    }
+    template <int SD>
+    bool launch_split(const SplitWeights &w, int M, int K, const double *Bsrc, long long bstride, int bit0, double *out,
+                      const double *bias_, const uint32_t *keys0, int Sc, int accumulate, const int *perm_, int chain,
+                      int n_chain, cudaStream_t cs)
+    {
+        const int tiles = (Sc + SP_BS - 1) / SP_BS;
+        const int mine = (tiles - chain + n_chain - 1) / n_chain;
+        if (mine <= 0) return false;
+        if (!w.ready) throw CudaFail{"weight digits were not prepared"};
+        SliceArgs sa{};
+        sa.src = Bsrc; sa.stride = bstride; sa.keys = keys0; sa.kw = kw; sa.bit0 = bit0; sa.K = K; sa.Kpad = w.Kpad;
+        sa.perm = perm_; sa.S = Sc; sa.dig = bdig.as<signed char>(); sa.pitch = (long long)b_pitch;
+        sa.slice_stride = (long long)(b_ncap * b_pitch); sa.scale = bscale.as<double>();
+        sa.tile_stride = n_chain; sa.tile_offset = chain;
+        slice_rows_kernel<SD><<<(unsigned)((Sc + 7) / 8), 256, 0, cs>>>(sa);
+        ++stats.n_launches;
+        SplitArgs g{};
+        g.k_steps = w.Kpad / SP_BK; g.M = M; g.m_tiles = w.Mpad / SP_BM; g.S = Sc; g.perm = perm_;
+        g.out = out; g.out_stride = 4LL * R; g.bias = bias_; g.scaleA = w.scale.as<double>();
+        g.scaleB = bscale.as<double>(); g.accumulate = accumulate; g.tile_stride = n_chain; g.tile_offset = chain;
+        split_gemm_kernel<SD><<<(unsigned)(g.m_tiles * mine), SP_THREADS, SplitCfg<SD>::SMEM, cs>>>(w.map, b_map(w.Kpad), g);
+        return true;
+    }
+
     void launch_gemm(const double *Wt_, int Mpad_, int M, int K, const double *Bsrc, long long bstride, int bit0,
                      double *out, const double *bias_, const uint32_t *keys0, int Sc, int accumulate, const int *perm_,
-                     int chain = 0, int n_chain = 1)
+                     int chain = 0, int n_chain = 1, const SplitWeights *sw = nullptr)
     {
         GemmArgs g{};
         g.Wt = Wt_; g.Mpad = Mpad_; g.M = M; g.K = K;
@@ -461,8 +587,16 @@ struct am_handle {
             compose_gemm_kernel<C><<<grid, C::THREADS, C::smem_bytes(K), cs>>>(g);
             launched = true;
         };
-        switch (gemm_variant) {   // AM_B200_GEMM_VARIANT: tuning knob, see DESIGN.md section 4
+        switch (gemm_variant) {   // AM_B200_GEMM_VARIANT: see DESIGN.md section 4
             case 1: go(GemmWide{}); break;
+            case 2:
+                if (sw == nullptr) throw CudaFail{"split GEMM without weight digits"};
+                switch (split_digits) {
+                    case 6: launched = launch_split<6>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs); break;
+                    case 8: launched = launch_split<8>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs); break;
+                    default: launched = launch_split<7>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs); break;
+                }
+                break;
             default: go(GemmDefault{}); break;
         }
         if (launched) ++stats.n_launches;
@@ -484,6 +618,7 @@ struct am_handle {
         // states).  The state tiles are dealt round-robin to n_chain independent chains on separate
         // streams, so the tail of one chain's launch is filled by the others' CTAs.
         const int n_chain = (D >= 3) ? (n_chains > 0 ? n_chains : (shard_world > 1 ? 4 : 1)) : 1;
+        if (gemm_variant == 2) ensure_split_scratch((size_t)S_all);
         const bool timed = timing_on();
         size_t span0 = 0;
         pending_gemm_flops = 0.0;
@@ -502,7 +637,7 @@ struct am_handle {
             for (int c = 0; c < n_chain; ++c) {
                 cudaStream_t cs = (n_chain > 1) ? chain_stream[c] : stream;
                 launch_gemm(Wt[h].as<double>(), Mpad[h], n[h + 1], n[h], Bsrc, bstride, off[h], out,
-                            bias[h].as<double>(), keys0, Sc, 0, prm, c, n_chain);
+                            bias[h].as<double>(), keys0, Sc, 0, prm, c, n_chain, gemm_variant == 2 ? &splitW[h] : nullptr);
                 for (const Skip &sk : skips[h]) {
                     const bool identity = (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0);
                     const int M = n[h + 1];
@@ -521,7 +656,8 @@ struct am_handle {
                             ++stats.n_launches;
                         } else {
                             launch_gemm(TMt[sk.tm].as<double>(), tm_Mpad[sk.tm], M, n[sk.src], src, sstride, off[sk.src],
-                                        out, nullptr, keys0, Sc, 1, prm, c, n_chain);
+                                        out, nullptr, keys0, Sc, 1, prm, c, n_chain,
+                                        gemm_variant == 2 ? &splitTM[sk.tm] : nullptr);
                         }
                     }
                     CK(cudaGetLastError());
@@ -663,6 +799,20 @@ void upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st)
     if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
 }
 
+void prepare_split_weights(am_handle *h, SplitWeights &sw, const double *w, int M, int K)
+{
+    sw.Kpad = (K + SP_KPAD - 1) / SP_KPAD * SP_KPAD;
+    sw.Mpad = (M + SP_BM - 1) / SP_BM * SP_BM;
+    std::vector<signed char> dig;
+    std::vector<double> scale;
+    split_weight_digits(w, M, K, sw.Mpad, sw.Kpad, h->split_digits, dig, scale);
+    upload(sw.dig, dig.data(), dig.size(), h->stream);
+    upload(sw.scale, scale.data(), scale.size() * 8, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    sw.map = make_digit_map(sw.dig.p, sw.Kpad, (size_t)sw.Kpad, (size_t)sw.Mpad, h->split_digits, SP_BM);
+    sw.ready = true;
+}
+
 int load_weights(am_handle *h, const void *const *W, const void *const *B, const void *const *TMp, const int *tm_shapes,
                  int n_tm)
 {
@@ -693,6 +843,7 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
         upload(h->Wt[l], wt.data(), wt.size() * 8, h->stream);
         upload(h->bias[l], b.data(), b.size() * 8, h->stream);
         CK(cudaStreamSynchronize(h->stream));
+        if (h->gemm_variant == 2) prepare_split_weights(h, h->splitW[l], w.data(), M, K);
     }
     {
         auto w = fetch_real(W[D], (size_t)h->n[D], h->f64);
@@ -702,6 +853,7 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
         CK(cudaStreamSynchronize(h->stream));
     }
     h->TM.resize(n_tm); h->TMt.resize(n_tm);
+    h->splitTM.resize(n_tm);
     h->tm_h.assign(n_tm, 0); h->tm_w.assign(n_tm, 0); h->tm_Mpad.assign(n_tm, 0);
     for (int t = 0; t < n_tm; ++t) {
         const int th = tm_shapes[2 * t], tw = tm_shapes[2 * t + 1];
@@ -716,6 +868,7 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
             for (int k = 0; k < tw; ++k) wt[(size_t)k * Mp + m] = w[(size_t)m * tw + k];
         upload(h->TMt[t], wt.data(), wt.size() * 8, h->stream);
         CK(cudaStreamSynchronize(h->stream));
+        if (h->gemm_variant == 2) prepare_split_weights(h, h->splitTM[t], w.data(), th, tw);
     }
     // shape checks of the skips (reference backend/src/cuam.cpp:153-173)
     for (int l = 1; l <= D; ++l)
@@ -1128,8 +1281,16 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
                 if (need > 227 * 1024) throw CudaFail{"hidden layers this wide are not supported by the composition kernel"};
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             };
+            if (const char *e = getenv("AM_B200_SPLIT_DIGITS")) h->split_digits = std::max(6, std::min(8, atoi(e)));
+            h->splitW.resize(h->D + 1);
             switch (h->gemm_variant) {
                 case 1: prep(GemmWide{}, compose_gemm_kernel<GemmWide>); break;
+                case 2:
+                    if (kmax > 8192) throw CudaFail{"hidden layers wider than 8192 overflow the int32 digit accumulators"};
+                    CK(cudaFuncSetAttribute(split_gemm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitCfg<6>::SMEM));
+                    CK(cudaFuncSetAttribute(split_gemm_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitCfg<7>::SMEM));
+                    CK(cudaFuncSetAttribute(split_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitCfg<8>::SMEM));
+                    break;
                 default: prep(GemmDefault{}, compose_gemm_kernel<GemmDefault>); break;
             }
         }

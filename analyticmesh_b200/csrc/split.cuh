@@ -1,0 +1,351 @@
+// split.cuh -- the affine-composition GEMM on the 5th-generation tensor cores (tcgen05, kind::i8).
+//
+// tcgen05 has no FP64 kind, so the FP64 contraction  P_out = W . diag(mask) . P_in  (compose.cuh) is
+// computed by an error-free integer split ("Ozaki scheme"): every row of W and every column of the
+// masked P_in is scaled by a power of two and cut into SD signed base-256 digits,
+//
+//        x  =  2^(e-6) * sum_t d_t 2^(-8t) + r,   d_t in [-128, 127],  |r| <= 2^(e - 8 SD + 1),  2^e > max |x|
+//
+// (e: one exponent per weight row / per plane column).  All digit products are exact in int32:
+// |d d'| <= 2^14, K <= 2^13 terms and <= SD products per accumulator stay below 2^31.  The digit planes
+// are multiplied pairwise on the tensor cores, products of equal weight 2^(-8 (i+j)) share one TMEM
+// accumulator D_g (g = i + j < SD), and the epilogue evaluates
+//
+//        out[m][n] = 2^(eA_m - 6) 2^(eB_n - 6) * ( ... (D_{SD-1} 2^-8 + D_{SD-2}) 2^-8 + ... + D_0 )  (+ bias)
+//
+// in FP64 (every step is one correctly rounded operation, so tests/split_emul.py reproduces the result
+// bit for bit on the CPU).  With SD = 7 the operands carry 54 bits below their row / column maximum,
+// i.e. the rounding of the result is at the level of an FP64 dot product; the dropped products
+// (i + j >= SD) are below 2^-50 of max|w| max|p| K.
+//
+// Kernel layout (one CTA per 128 output neurons x 16 states tile, 192 threads):
+//   warp 0    TMA producer: per 32-byte K step one 3-D box of the weight digits [SD][128][32] and one of
+//             the plane digits [SD][64][32] (SWIZZLE_32B), multi-stage mbarrier ring
+//   warp 1    TMEM allocation (512 columns) + single-thread MMA issue: for weight digit i ONE
+//             instruction covers the plane digits j = 0 .. SD-1-i, because their accumulators
+//             g = i + j are adjacent 64-column windows of TMEM (N = 64 (SD - i), cut at 256)
+//   warps 2-5 epilogue: tcgen05.ld of the SD accumulators, FP64 Horner, scale, bias, 16-byte stores
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace amb {
+
+constexpr int SP_BM = 128;        // output neurons per tile (TMEM lanes)
+constexpr int SP_BS = 16;         // states per tile
+constexpr int SP_BN = SP_BS * 4;  // columns per tile
+constexpr int SP_BK = 32;         // K bytes per pipeline stage = K of one kind::i8 instruction
+constexpr int SP_THREADS = 192;
+constexpr int SP_KPAD = 32;       // digit rows are padded to a multiple of this many K bytes
+
+template <int SD>
+struct SplitCfg {
+    static constexpr int STAGE_A = SD * SP_BM * SP_BK;
+    static constexpr int STAGE_B = SD * SP_BN * SP_BK;
+    static constexpr int STAGE = STAGE_A + STAGE_B;
+    static constexpr int STAGES = (215 * 1024) / STAGE;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int FRAC_BITS = 8 * SD - 2;         // |X| = |x| 2^(FRAC_BITS - e) <= 2^FRAC_BITS
+    static constexpr size_t SMEM = size_t(STAGES) * STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
+    static_assert(SD * SP_BN <= TMEM_COLS, "accumulators exceed TMEM");
+    static_assert(STAGE % 1024 == 0 && STAGE_A % 1024 == 0, "stage bases must keep the swizzle alignment");
+};
+
+// ---- host + device: digits of one value ------------------------------------------------------------
+// X = rint(x * 2^(FRAC - e)) as a signed integer; digit t (t = 0 most significant) is byte (SD-1-t)
+// of  (X + 0x80..80) ^ 0x80..80  read as int8:  X = sum_t d_t 256^(SD-1-t).
+__host__ __device__ inline unsigned long long split_pack(long long X, int SD)
+{
+    const unsigned long long C = (SD >= 8) ? 0x8080808080808080ull : (0x8080808080808080ull >> (8 * (8 - SD)));
+    return ((unsigned long long)X + C) ^ C;
+}
+
+// ---- plane digits (B operand), one warp per state slot ------------------------------------------------
+struct SliceArgs {
+    const double *src;          // rows of the input layer for state 0: [K][4]
+    long long stride;           // doubles between states (0: the shared layer-1 table)
+    const uint32_t *keys;
+    int kw, bit0, K, Kpad;      // Kpad: K rounded up to SP_KPAD (the padding digits are written as zeros)
+    const int *perm;            // slot -> state (nullptr = identity)
+    int S;                      // slots
+    signed char *dig;           // [SD][ncap][pitch], column n = slot * 4 + component
+    long long pitch;            // bytes between columns (>= Kpad)
+    long long slice_stride;     // bytes between digit planes (ncap * pitch)
+    double *scale;              // [S * 4]  2^(e - 6)
+    int tile_stride, tile_offset;   // this launch handles the slots of tiles tile_offset, tile_offset + tile_stride, ...
+};
+
+template <int SD>
+__global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a)
+{
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= a.S || (slot / SP_BS) % a.tile_stride != a.tile_offset) return;
+    const int s = a.perm ? a.perm[slot] : slot;
+    const double *rows = a.src + (size_t)s * a.stride;
+    const uint32_t *key = a.keys + (size_t)s * a.kw;
+
+    auto active = [&](int k) -> bool {
+        const int bit = a.bit0 + k;
+        return k < a.K && ((key[bit >> 5] >> (bit & 31)) & 1u);
+    };
+    // pass 1: per component, max |x| over the active rows
+    double mx[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = lane * 4; k0 < a.K; k0 += 128) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            if (active(k)) {
+                const double2 p = *reinterpret_cast<const double2 *>(rows + (size_t)k * 4);
+                const double2 q = *reinterpret_cast<const double2 *>(rows + (size_t)k * 4 + 2);
+                mx[0] = fmax(mx[0], fabs(p.x)); mx[1] = fmax(mx[1], fabs(p.y));
+                mx[2] = fmax(mx[2], fabs(q.x)); mx[3] = fmax(mx[3], fabs(q.y));
+            }
+        }
+    }
+    double mul[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx[c] = fmax(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        int e = 0;
+        if (mx[c] > 0.0 && mx[c] < 1.7e308) frexp(mx[c], &e);          // mx = f 2^e, f in [0.5, 1)
+        mul[c] = ldexp(1.0, SplitCfg<SD>::FRAC_BITS - e);
+        if (lane == 0) a.scale[(size_t)slot * 4 + c] = ldexp(1.0, e - 6);
+    }
+    // pass 2: digits; lane owns 4 consecutive k -> one 32-bit store per (digit, component)
+    signed char *col0 = a.dig + (size_t)slot * 4 * a.pitch;
+    for (int k0 = lane * 4; k0 < a.Kpad; k0 += 128) {
+        unsigned long long Y[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            double v[4] = {0.0, 0.0, 0.0, 0.0};
+            if (active(k)) {
+                const double2 p = *reinterpret_cast<const double2 *>(rows + (size_t)k * 4);
+                const double2 q = *reinterpret_cast<const double2 *>(rows + (size_t)k * 4 + 2);
+                v[0] = p.x; v[1] = p.y; v[2] = q.x; v[3] = q.y;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Y[j][c] = split_pack(__double2ll_rn(v[c] * mul[c]), SD);
+        }
+#pragma unroll
+        for (int t = 0; t < SD; ++t) {
+            const int p = SD - 1 - t;                                     // byte of Y holding digit t
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w |= (uint32_t)((Y[j][c] >> (8 * p)) & 0xFFull) << (8 * j);
+                *reinterpret_cast<uint32_t *>(col0 + (size_t)t * a.slice_stride + (size_t)c * a.pitch + k0) = w;
+            }
+        }
+    }
+}
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SPLIT_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SPLIT_DONE_%=;\n\t"
+        "bra SPLIT_WAIT_%=;\n\t"
+        "SPLIT_DONE_%=:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major operand, rows of 32 bytes, SWIZZLE_32B: 8-row groups are 256 B apart (SBO); version 1 (sm_100)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr)
+{
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(256 >> 4) << 32) | (uint64_t(1) << 46) |
+           (uint64_t(6) << 61);
+}
+// kind::i8 instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t tc_idesc_i8(int n)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(SP_BM >> 4) << 24);
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+struct SplitArgs {
+    int k_steps;                // Kpad / 32
+    int M, m_tiles, S;          // output neurons, M tiles, state slots of the launch
+    const int *perm;            // slot -> state
+    double *out;                // rows of the output layer for state 0: [M][4]
+    long long out_stride;       // doubles between states
+    const double *bias;         // [M] or nullptr
+    const double *scaleA;       // [Mpad]   2^(eA - 6)
+    const double *scaleB;       // [S * 4]  2^(eB - 6)
+    int accumulate;             // out += result
+    int tile_stride, tile_offset;
+};
+
+template <int SD>
+__global__ void __launch_bounds__(SP_THREADS, 1)
+split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SplitArgs a)
+{
+    using C = SplitCfg<SD>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + C::STAGES * C::STAGE;               // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::STAGES, bar_tmem = bars + 16 * C::STAGES;
+    const uint32_t tmem_slot = bar_tmem + 8;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = (blockIdx.x % a.m_tiles) * SP_BM;                 // m fastest: CTAs sharing plane digits are co-resident
+    const int tile = (blockIdx.x / a.m_tiles) * a.tile_stride + a.tile_offset;
+    const int s0 = tile * SP_BS;
+    const int KS = a.k_steps;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::STAGES; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "n"(C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ks = 0; ks < KS; ++ks) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                const uint32_t sa = base + stage * C::STAGE, sb = sa + C::STAGE_A;
+                mbar_expect_tx(bar_full + 8 * stage, C::STAGE);
+                tma_load_3d(sa, &tmA, ks * SP_BK, m0, 0, bar_full + 8 * stage);
+                tma_load_3d(sb, &tmB, ks * SP_BK, s0 * 4, 0, bar_full + 8 * stage);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ks = 0; ks < KS; ++ks) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t sa = base + stage * C::STAGE, sb = sa + C::STAGE_A;
+#pragma unroll
+                for (int i = 0; i < SD; ++i) {
+                    const uint64_t adesc = tc_smem_desc(sa + i * (SP_BM * SP_BK));
+                    const int n_total = (SD - i) * SP_BN;
+#pragma unroll
+                    for (int c0 = 0; c0 < n_total; c0 += 256) {
+                        const int n = (n_total - c0 < 256) ? (n_total - c0) : 256;
+                        tc_mma_i8(tmem + (uint32_t)(i * SP_BN + c0), adesc, tc_smem_desc(sb + c0 * SP_BK), tc_idesc_i8(n),
+                                  (ks > 0 || i > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar_empty + 8 * stage);                    // frees the stage once its MMAs have read it
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            }
+            tc_commit(bar_tmem);                                     // accumulators complete
+        }
+    } else {
+        // ---- epilogue: this warp reads TMEM lanes [32 q, 32 q + 32), q = warp % 4 ------------------------
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        const bool m_ok = m < a.M;
+        const double sA = m_ok ? a.scaleA[m] : 0.0;
+        const double bias = (m_ok && a.bias != nullptr) ? a.bias[m] : 0.0;
+        mbar_wait(bar_tmem, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int cb = 0; cb < SP_BN / 16; ++cb) {
+            int v[SD][16];
+#pragma unroll
+            for (int g = 0; g < SD; ++g) tc_ld16(trow + (uint32_t)(g * SP_BN + cb * 16), v[g]);
+            tc_ld_wait();
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+                const int slot = s0 + cb * 4 + st;
+                if (slot >= a.S || !m_ok) continue;
+                const int s = a.perm ? a.perm[slot] : slot;
+                const double4 sB = *reinterpret_cast<const double4 *>(a.scaleB + (size_t)slot * 4);
+                const double sb[4] = {sB.x, sB.y, sB.z, sB.w};
+                double r[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    double acc = (double)v[SD - 1][st * 4 + c];
+#pragma unroll
+                    for (int g = SD - 2; g >= 0; --g) acc = fma(acc, 0.00390625, (double)v[g][st * 4 + c]);
+                    r[c] = acc * sA * sb[c];
+                }
+                r[3] += bias;
+                double2 *dst = reinterpret_cast<double2 *>(a.out + (size_t)s * a.out_stride + (size_t)m * 4);
+                if (a.accumulate) {
+                    const double2 o0 = dst[0], o1 = dst[1];
+                    r[0] = o0.x + r[0]; r[1] = o0.y + r[1]; r[2] = o1.x + r[2]; r[3] = o1.y + r[3];
+                }
+                dst[0] = make_double2(r[0], r[1]);
+                dst[1] = make_double2(r[2], r[3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace amb
