@@ -333,6 +333,7 @@ struct am_handle {
     // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
     int gemm_variant = 0;                       // 0/1: FP64 DMMA tiles, 2: tcgen05 int8 split (split.cuh)
     int split_digits = 7;
+    int num_sms = 148;
     std::vector<SplitWeights> splitW, splitTM;  // index h = 1..D-1 / transform index
     DevBuf bdig, bscale;                        // plane digits [SD][b_ncap][b_pitch] and column scales of the current launch
     size_t b_ncap = 0, b_pitch = 0;
@@ -560,7 +561,9 @@ struct am_handle {
         g.k_steps = w.Kpad / SP_BK; g.M = M; g.m_tiles = w.Mpad / SP_BM; g.S = Sc; g.perm = perm_;
         g.out = out; g.out_stride = 4LL * R; g.bias = bias_; g.scaleA = w.scale.as<double>();
         g.scaleB = bscale.as<double>(); g.accumulate = accumulate; g.tile_stride = n_chain; g.tile_offset = chain;
-        split_gemm_kernel<SD><<<(unsigned)(g.m_tiles * mine), SP_THREADS, SplitCfg<SD>::SMEM, cs>>>(w.map, b_map(w.Kpad), g);
+        g.n_tiles = g.m_tiles * mine;
+        split_gemm_kernel<SD><<<(unsigned)std::min(g.n_tiles, num_sms), SP_THREADS, SplitCfg<SD>::SMEM, cs>>>(
+            w.map, b_map(w.Kpad), g);
         return true;
     }
 
@@ -1283,6 +1286,11 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
             };
             if (const char *e = getenv("AM_B200_SPLIT_DIGITS")) h->split_digits = std::max(6, std::min(8, atoi(e)));
             h->splitW.resize(h->D + 1);
+            {
+                int dev = 0;
+                CK(cudaGetDevice(&dev));
+                CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
+            }
             switch (h->gemm_variant) {
                 case 1: prep(GemmWide{}, compose_gemm_kernel<GemmWide>); break;
                 case 2:

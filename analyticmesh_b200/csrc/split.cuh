@@ -47,7 +47,7 @@ struct SplitCfg {
     static constexpr int STAGES = (215 * 1024) / STAGE;
     static constexpr int TMEM_COLS = 512;
     static constexpr int FRAC_BITS = 8 * SD - 2;         // |X| = |x| 2^(FRAC_BITS - e) <= 2^FRAC_BITS
-    static constexpr size_t SMEM = size_t(STAGES) * STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr size_t SMEM = size_t(STAGES) * STAGE + 1024 /* alignment slack */ + 2048 /* barriers, tile constants */;
     static_assert(SD * SP_BN <= TMEM_COLS, "accumulators exceed TMEM");
     static_assert(STAGE % 1024 == 0 && STAGE_A % 1024 == 0, "stage bases must keep the swizzle alignment");
 };
@@ -213,6 +213,7 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 struct SplitArgs {
     int k_steps;                // Kpad / 32
     int M, m_tiles, S;          // output neurons, M tiles, state slots of the launch
+    int n_tiles;                // tiles of this launch = m_tiles * (state tiles dealt to this chain)
     const int *perm;            // slot -> state
     double *out;                // rows of the output layer for state 0: [M][4]
     long long out_stride;       // doubles between states
@@ -223,22 +224,32 @@ struct SplitArgs {
     int tile_stride, tile_offset;
 };
 
+// exact int32 -> double on the FP64 pipe (LOP3 + DADD; I2F.F64 runs at a quarter of that rate)
+__device__ __forceinline__ double i32_to_f64(int x)
+{
+    return __hiloint2double(0x43300000, (int)((unsigned)x ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
+// Persistent: gridDim.x CTAs (one per SM) stride over the tiles; the TMA producer runs ahead into the next
+// tile while the epilogue drains TMEM, TMEM / barriers are set up once per CTA.
 template <int SD>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SplitArgs a)
 {
     using C = SplitCfg<SD>;
     extern __shared__ unsigned char smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + C::STAGES * C::STAGE;               // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::STAGES, bar_tmem = bars + 16 * C::STAGES;
-    const uint32_t tmem_slot = bar_tmem + 8;
-    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const uint32_t raw0 = smem_u32(smem_raw);
+    const uint32_t base = (raw0 + 1023u) & ~1023u;
+    // after the stages: full[STAGES], empty[STAGES], tmem_full, tmem_empty, tmem_ptr | perm[2][16] | scaleB[2][64]
+    const uint32_t bars = base + C::STAGES * C::STAGE;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::STAGES, bar_tfull = bars + 16 * C::STAGES;
+    const uint32_t bar_tempty = bar_tfull + 8, tmem_slot = bar_tfull + 16;
+    unsigned char *tail = smem_raw + (bars - raw0);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(tail + 16 * C::STAGES + 16);
+    int *s_perm = reinterpret_cast<int *>(tail + 16 * C::STAGES + 32);                 // [2][SP_BS]
+    double *s_scale = reinterpret_cast<double *>(tail + 16 * C::STAGES + 32 + 128);    // [2][SP_BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = (blockIdx.x % a.m_tiles) * SP_BM;                 // m fastest: CTAs sharing plane digits are co-resident
-    const int tile = (blockIdx.x / a.m_tiles) * a.tile_stride + a.tile_offset;
-    const int s0 = tile * SP_BS;
     const int KS = a.k_steps;
 
     if (threadIdx.x == 0) {
@@ -246,7 +257,8 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
-        mbar_init(bar_tmem, 1);
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 4);                                    // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -265,78 +277,102 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (int ks = 0; ks < KS; ++ks) {
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-                const uint32_t sa = base + stage * C::STAGE, sb = sa + C::STAGE_A;
-                mbar_expect_tx(bar_full + 8 * stage, C::STAGE);
-                tma_load_3d(sa, &tmA, ks * SP_BK, m0, 0, bar_full + 8 * stage);
-                tma_load_3d(sb, &tmB, ks * SP_BK, s0 * 4, 0, bar_full + 8 * stage);
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const int m0 = (t % a.m_tiles) * SP_BM;              // m fastest: CTAs sharing plane digits run together
+                const int n0 = ((t / a.m_tiles) * a.tile_stride + a.tile_offset) * SP_BN;
+                for (int ks = 0; ks < KS; ++ks) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                    const uint32_t sa = base + stage * C::STAGE, sb = sa + C::STAGE_A;
+                    mbar_expect_tx(bar_full + 8 * stage, C::STAGE);
+                    tma_load_3d(sa, &tmA, ks * SP_BK, m0, 0, bar_full + 8 * stage);
+                    tma_load_3d(sb, &tmB, ks * SP_BK, n0, 0, bar_full + 8 * stage);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
-            for (int ks = 0; ks < KS; ++ks) {
-                mbar_wait(bar_full + 8 * stage, phase);
+            uint32_t phase = 0, tphase = 0;
+            for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                mbar_wait(bar_tempty, tphase ^ 1u);                  // the epilogue has drained the previous tile
                 tc_fence_after();
-                const uint32_t sa = base + stage * C::STAGE, sb = sa + C::STAGE_A;
+                for (int ks = 0; ks < KS; ++ks) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * C::STAGE, sb = sa + C::STAGE_A;
 #pragma unroll
-                for (int i = 0; i < SD; ++i) {
-                    const uint64_t adesc = tc_smem_desc(sa + i * (SP_BM * SP_BK));
-                    const int n_total = (SD - i) * SP_BN;
+                    for (int i = 0; i < SD; ++i) {
+                        const uint64_t adesc = tc_smem_desc(sa + i * (SP_BM * SP_BK));
+                        const int n_total = (SD - i) * SP_BN;
 #pragma unroll
-                    for (int c0 = 0; c0 < n_total; c0 += 256) {
-                        const int n = (n_total - c0 < 256) ? (n_total - c0) : 256;
-                        tc_mma_i8(tmem + (uint32_t)(i * SP_BN + c0), adesc, tc_smem_desc(sb + c0 * SP_BK), tc_idesc_i8(n),
-                                  (ks > 0 || i > 0) ? 1u : 0u);
+                        for (int c0 = 0; c0 < n_total; c0 += 256) {
+                            const int n = (n_total - c0 < 256) ? (n_total - c0) : 256;
+                            tc_mma_i8(tmem + (uint32_t)(i * SP_BN + c0), adesc, tc_smem_desc(sb + c0 * SP_BK), tc_idesc_i8(n),
+                                      (ks > 0 || i > 0) ? 1u : 0u);
+                        }
                     }
+                    tc_commit(bar_empty + 8 * stage);                // frees the stage once its MMAs have read it
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(bar_empty + 8 * stage);                    // frees the stage once its MMAs have read it
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+                tc_commit(bar_tfull);                                // accumulators of this tile complete
+                tphase ^= 1u;
             }
-            tc_commit(bar_tmem);                                     // accumulators complete
         }
     } else {
         // ---- epilogue: this warp reads TMEM lanes [32 q, 32 q + 32), q = warp % 4 ------------------------
         const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
-        const bool m_ok = m < a.M;
-        const double sA = m_ok ? a.scaleA[m] : 0.0;
-        const double bias = (m_ok && a.bias != nullptr) ? a.bias[m] : 0.0;
-        mbar_wait(bar_tmem, 0);
-        tc_fence_after();
+        const int e = threadIdx.x - 64;                              // 0..127
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t tphase = 0;
+        int buf = 0;
+        for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, buf ^= 1) {
+            const int m0 = (t % a.m_tiles) * SP_BM;
+            const int s0 = ((t / a.m_tiles) * a.tile_stride + a.tile_offset) * SP_BS;
+            // tile constants -> shared memory, hidden behind the tile's MMAs
+            if (e < SP_BS) s_perm[buf * SP_BS + e] = (s0 + e < a.S) ? (a.perm ? a.perm[s0 + e] : s0 + e) : -1;
+            if (e < SP_BN) s_scale[buf * SP_BN + e] = (s0 + (e >> 2) < a.S) ? a.scaleB[(size_t)s0 * 4 + e] : 0.0;
+            const int m = m0 + q * 32 + lane;
+            const bool m_ok = m < a.M;
+            const double sA = m_ok ? a.scaleA[m] : 0.0;
+            const double bias = (m_ok && a.bias != nullptr) ? a.bias[m] : 0.0;
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            mbar_wait(bar_tfull, tphase);
+            tphase ^= 1u;
+            tc_fence_after();
 #pragma unroll 1
-        for (int cb = 0; cb < SP_BN / 16; ++cb) {
-            int v[SD][16];
+            for (int cb = 0; cb < SP_BN / 16; ++cb) {
+                int v[SD][16];
 #pragma unroll
-            for (int g = 0; g < SD; ++g) tc_ld16(trow + (uint32_t)(g * SP_BN + cb * 16), v[g]);
-            tc_ld_wait();
-#pragma unroll
-            for (int st = 0; st < 4; ++st) {
-                const int slot = s0 + cb * 4 + st;
-                if (slot >= a.S || !m_ok) continue;
-                const int s = a.perm ? a.perm[slot] : slot;
-                const double4 sB = *reinterpret_cast<const double4 *>(a.scaleB + (size_t)slot * 4);
-                const double sb[4] = {sB.x, sB.y, sB.z, sB.w};
-                double r[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    double acc = (double)v[SD - 1][st * 4 + c];
-#pragma unroll
-                    for (int g = SD - 2; g >= 0; --g) acc = fma(acc, 0.00390625, (double)v[g][st * 4 + c]);
-                    r[c] = acc * sA * sb[c];
+                for (int g = 0; g < SD; ++g) tc_ld16(trow + (uint32_t)(g * SP_BN + cb * 16), v[g]);
+                tc_ld_wait();
+                if (cb == SP_BN / 16 - 1) {                          // TMEM fully read: the next tile's MMAs may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_tempty) : "memory");
                 }
-                r[3] += bias;
-                double2 *dst = reinterpret_cast<double2 *>(a.out + (size_t)s * a.out_stride + (size_t)m * 4);
-                if (a.accumulate) {
-                    const double2 o0 = dst[0], o1 = dst[1];
-                    r[0] = o0.x + r[0]; r[1] = o0.y + r[1]; r[2] = o1.x + r[2]; r[3] = o1.y + r[3];
+#pragma unroll
+                for (int st = 0; st < 4; ++st) {
+                    const int s = s_perm[buf * SP_BS + cb * 4 + st];
+                    if (s < 0 || !m_ok) continue;
+                    const double *sb = s_scale + buf * SP_BN + cb * 16 + st * 4;
+                    double r[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        double acc = i32_to_f64(v[SD - 1][st * 4 + c]);
+#pragma unroll
+                        for (int g = SD - 2; g >= 0; --g) acc = fma(acc, 0.00390625, i32_to_f64(v[g][st * 4 + c]));
+                        r[c] = acc * sA * sb[c];
+                    }
+                    r[3] += bias;
+                    double2 *dst = reinterpret_cast<double2 *>(a.out + (size_t)s * a.out_stride + (size_t)m * 4);
+                    if (a.accumulate) {
+                        const double2 o0 = dst[0], o1 = dst[1];
+                        r[0] = o0.x + r[0]; r[1] = o0.y + r[1]; r[2] = o1.x + r[2]; r[3] = o1.y + r[3];
+                    }
+                    dst[0] = make_double2(r[0], r[1]);
+                    dst[1] = make_double2(r[2], r[3]);
                 }
-                dst[0] = make_double2(r[0], r[1]);
-                dst[1] = make_double2(r[2], r[3]);
             }
         }
     }
