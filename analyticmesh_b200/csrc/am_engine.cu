@@ -366,6 +366,10 @@ struct am_handle {
     std::vector<long long> h_face_off;
     double gemm_ms = 0.0, gemm_flops = 0.0;
     long long gemm_launches = 0;
+    // span kinds: 0 composition chain of a chunk, 1 compose phase, 2 clip, 3 frontier, 4 tensor GEMM kernel, 5 digit kernel
+    static constexpr int N_KINDS = 8;
+    double kind_ms[N_KINDS] = {}, kind_flops[N_KINDS] = {};
+    long long kind_launches[N_KINDS] = {};
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     struct Span { size_t a, b; int kind; double flops; };
@@ -555,15 +559,21 @@ struct am_handle {
         sa.perm = perm_; sa.S = Sc; sa.dig = bdig.as<signed char>(); sa.pitch = (long long)b_pitch;
         sa.slice_stride = (long long)(b_ncap * b_pitch); sa.scale = bscale.as<double>();
         sa.tile_stride = n_chain; sa.tile_offset = chain;
+        const bool t = timing_on() && n_chain == 1;      // per-kernel events (the roofline of the dominant kernel)
+        size_t e0 = 0;
+        if (t) e0 = span_begin();
         slice_rows_kernel<SD><<<(unsigned)((Sc + 7) / 8), 256, 0, cs>>>(sa);
         ++stats.n_launches;
+        if (t) span_end(e0, 5, 0.0);
         SplitArgs g{};
         g.k_steps = w.Kpad / SP_BK; g.M = M; g.m_tiles = w.Mpad / SP_BM; g.S = Sc; g.perm = perm_;
         g.out = out; g.out_stride = 4LL * R; g.bias = bias_; g.scaleA = w.scale.as<double>();
         g.scaleB = bscale.as<double>(); g.accumulate = accumulate; g.tile_stride = n_chain; g.tile_offset = chain;
         g.n_tiles = g.m_tiles * mine;
+        if (t) e0 = span_begin();
         split_gemm_kernel<SD><<<(unsigned)std::min(g.n_tiles, num_sms), SP_THREADS, SplitCfg<SD>::SMEM, cs>>>(
             w.map, b_map(w.Kpad), g);
+        if (t) span_end(e0, 4, 2.0 * M * (double)K * 4.0 * Sc);
         return true;
     }
 
@@ -620,7 +630,7 @@ struct am_handle {
         // The layer launches of one chunk form a dependency chain (layer h+1 reads layer h of the same
         // states).  The state tiles are dealt round-robin to n_chain independent chains on separate
         // streams, so the tail of one chain's launch is filled by the others' CTAs.
-        const int n_chain = (D >= 3) ? (n_chains > 0 ? n_chains : (shard_world > 1 ? 4 : 1)) : 1;
+        const int n_chain = (D >= 3) ? (n_chains > 0 ? n_chains : ((shard_world > 1 && gemm_variant != 2) ? 4 : 1)) : 1;
         if (gemm_variant == 2) ensure_split_scratch((size_t)S_all);
         const bool timed = timing_on();
         size_t span0 = 0;
@@ -1191,12 +1201,16 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
 
 void resolve_spans(am_handle *h)
 {
-    double ms_k[4] = {0, 0, 0, 0};
+    double ms_k[am_handle::N_KINDS] = {};
     h->gemm_ms = 0; h->gemm_flops = 0; h->gemm_launches = 0;
+    for (int k = 0; k < am_handle::N_KINDS; ++k) h->kind_ms[k] = h->kind_flops[k] = 0.0, h->kind_launches[k] = 0;
     for (const auto &s : h->spans) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev_pool[s.a], h->ev_pool[s.b]) != cudaSuccess) { cudaGetLastError(); continue; }
         ms_k[s.kind] += ms;
+        h->kind_ms[s.kind] += ms;
+        h->kind_flops[s.kind] += s.flops;
+        h->kind_launches[s.kind]++;
         if (s.kind == 0) { h->gemm_flops += s.flops; h->gemm_launches++; }
     }
     h->gemm_ms = ms_k[0];
@@ -1278,6 +1292,8 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         {
             int kmax = 3;
             for (int l = 1; l <= h->D; ++l) kmax = std::max(kmax, h->n[l]);
+            // default: wide layers go to the tcgen05 split-integer path, narrow ones (tiles mostly padding) to FP64 DMMA
+            h->gemm_variant = (kmax >= 256) ? 2 : 0;   // measured: 128-wide 16.2 (DMMA) vs 10.0 M faces/s, 500-wide 12.6 vs 15.5
             if (const char *e = getenv("AM_B200_GEMM_VARIANT")) h->gemm_variant = atoi(e);
             auto prep = [&](auto cfg, auto kern) {
                 const size_t need = decltype(cfg)::smem_bytes(kmax);
@@ -1761,6 +1777,22 @@ double am_fp64_peak_tflops(void)
     cudaFree(out);
     if (best <= 0.f) return -1.0;
     return 2.0 * 8 * iters * (double)threads * blocks / (best * 1e-3) / 1e12;
+}
+
+int am_gemm_variant(const am_handle *h, int *split_digits)
+{
+    if (!h) return AM_ERR_ARG;
+    if (split_digits) *split_digits = h->split_digits;
+    return h->gemm_variant;
+}
+
+int am_kernel_profile(const am_handle *h, int kind, double *ms_total, int64_t *launches, double *flops)
+{
+    if (!h || kind < 0 || kind >= am_handle::N_KINDS) return AM_ERR_ARG;
+    if (ms_total) *ms_total = h->kind_ms[kind];
+    if (launches) *launches = h->kind_launches[kind];
+    if (flops) *flops = h->kind_flops[kind];
+    return AM_OK;
 }
 
 int am_compose_profile(const am_handle *h, double *ms_total, int64_t *launches, double *flops)

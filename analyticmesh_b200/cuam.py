@@ -37,7 +37,7 @@ class AmStats(ctypes.Structure):
 
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",
            "am_key_words", "am_state_len", "am_copy_states", "am_copy_faces", "am_copy_mesh", "am_load_weights",
-           "am_debug_planes", "am_compose_profile", "am_fp64_peak_tflops", "am_set_shard", "am_nccl_unique_id",
+           "am_debug_planes", "am_compose_profile", "am_kernel_profile", "am_gemm_variant", "am_fp64_peak_tflops", "am_set_shard", "am_nccl_unique_id",
            "am_set_shard_nccl", "am_ply_parse_faces",
            "am_ply_pack_faces")
 
@@ -231,6 +231,21 @@ def compose_profile():
     ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
     _err(lib().am_compose_profile(_handle, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)), "compose_profile")
     return dict(ms_total=ms.value, launches=n.value, flops=fl.value)
+
+
+def kernel_profile(kind):
+    """Device ms / launches / flops of one timed span kind of the last march (include/am_b200.h: am_kernel_profile)."""
+    ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+    _err(lib().am_kernel_profile(_handle, int(kind), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)),
+         "kernel_profile")
+    return dict(ms_total=ms.value, launches=n.value, flops=fl.value)
+
+
+def gemm_variant():
+    """(variant, split digits): 0/1 FP64 DMMA tiles, 2 tcgen05 int8 split-integer path."""
+    d = ctypes.c_int()
+    lib().am_gemm_variant.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    return int(lib().am_gemm_variant(_handle, ctypes.byref(d))), d.value
 
 
 def states():

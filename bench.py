@@ -62,6 +62,44 @@ def flops_per_face(nodes):
     return 8 * sum(h[i] * h[i - 1] for i in range(1, len(h))) + 8 * h[-1]
 
 
+def roofline(variant, split_digits, achieved, fp64_peak, launches, ms, flops):
+    """Dominant kernel against its bound.  FP64 DMMA path: the measured DFMA/DMMA pipe peak.  tcgen05 path
+    (SURVEY 8d): the int8 tensor peak divided by the number of digit products, with int8 = 2 x the bf16 rate
+    measured by the driver (MEASURED_PEAKS.json, sustained figure: the kernel is timed inside a long step)."""
+    avg_ms = ms / max(launches, 1)
+    if variant != 2:
+        traffic = ncu_traffic("compose_gemm_kernel", flops / max(launches, 1))
+        return {"bound": "fp64", "kernel": "compose_gemm_kernel", "achieved": achieved, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                "launches": launches, "avg_launch_ms": avg_ms,
+                "peak_source": "DFMA loop measured in this process (am_fp64_peak_tflops); FP64 is not in "
+                               "MEASURED_PEAKS.json; tools/fp64_peak.cu: DFMA 37.0, DMMA 37.0, cuBLAS DGEMM 35.8"}
+    products = split_digits * (split_digits + 1) // 2
+    bf16, src = 1400.0, "fallback of /opt/skills/guides/B200_PROFILING.md (sustained bf16 1.4 PFLOP/s)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        bf16, src = float(mp["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    except Exception:
+        pass
+    peak = 2.0 * bf16 / products
+    return {"bound": "tensor", "kernel": "split_gemm_kernel", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic("split_gemm_kernel", flops / max(launches, 1)),
+            "launches": launches, "avg_launch_ms": avg_ms,
+            "int8_tops_achieved": achieved * products, "int8_tops_peak": 2.0 * bf16, "digit_products": products,
+            "peak_source": f"FP64-equivalent TFLOP/s: algorithmic 2*M*K*4*S flops of the launch; peak = int8 tensor peak / "
+                           f"{products} digit products, int8 peak = 2 x {src} ({bf16:.0f})"}
+
+
+def ncu_traffic(kernel, flops_per_launch):
+    """DRAM bytes per launch of the dominant kernel, scaled from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json: dram bytes and algorithmic flops of the captured launches)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return t["dram_bytes"] / t["flops"] * flops_per_launch
+    except Exception:
+        return None
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -209,6 +247,8 @@ def main():
     faces = launches = 0
     gemm_ms = gemm_flops = 0.0
     gemm_launches = 0
+    variant, split_digits = cuam.gemm_variant()
+    prof_kind = 4 if variant == 2 else None       # the tcgen05 GEMM kernel alone, else the FP64 DMMA launches
     engine_s = 0.0
     last = None
     for _ in range(args.steps):
@@ -217,7 +257,9 @@ def main():
         launches += last["n_launches"]
         engine_s += last["seconds_march"]
         phases = {k: last[k] for k in ("seconds_compose", "seconds_clip", "seconds_frontier")}
-        p = cuam.compose_profile()
+        p = cuam.kernel_profile(prof_kind) if prof_kind is not None else cuam.compose_profile()
+        if prof_kind is not None and p["launches"] == 0:      # multi-chain mode records no per-kernel events
+            p = cuam.compose_profile()
         gemm_ms += p["ms_total"]
         gemm_flops += p["flops"]
         gemm_launches += p["launches"]
@@ -285,15 +327,14 @@ def main():
                                        "export_time": export_time, "ply_bytes": ply_bytes},
                        "engine_stream_seconds_per_step": engine_s / args.steps,
                        "phase_seconds_last_step_rank0": phases,
-                       "algorithmic_flops_per_face": fpf},
+                       "algorithmic_flops_per_face": fpf,
+                       "arithmetic": (f"FP64 planes; contraction as {split_digits} x {split_digits} signed 8-bit digit planes on "
+                                      "tcgen05 kind::i8 with exact int32 accumulation, FP64 recombination"
+                                      if variant == 2 else "FP64 tensor-core DMMA")},
             "e2e": {"value": e_faces / e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "compose_gemm_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
-                         "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
-                         "peak_source": "DFMA loop measured in this process (am_fp64_peak_tflops); FP64 is not in "
-                                        "MEASURED_PEAKS.json; tools/fp64_peak.cu: DFMA 37.0, DMMA 37.0, cuBLAS DGEMM 35.8"},
+            "roofline": roofline(variant, split_digits, achieved, peak, gemm_launches, gemm_ms, gemm_flops),
         }
         if world == 1 and not args.no_cpu_baseline:
             f, s, n = cpu_reference_sample(info, points, states, args.ref_states)

@@ -137,6 +137,13 @@ int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, 
  * its launches in the last march, its launch count and the flops of those launches. */
 int am_compose_profile(const am_handle *h, double *ms_total, int64_t *launches, double *flops);
 
+/* same, per timed span kind: 0 composition launches of a chunk (= am_compose_profile), 1 compose phase,
+ * 2 clip, 3 frontier, 4 the tcgen05 split-integer GEMM kernel alone, 5 its digit-extraction kernel.
+ * Kinds 4/5 are recorded per launch with CUDA events on the engine's stream (single-chain mode). */
+int am_kernel_profile(const am_handle *h, int kind, double *ms_total, int64_t *launches, double *flops);
+/* 0/1: FP64 tensor-core (DMMA) tiles, 2: tcgen05 int8 split-integer path; digits of the split (6..8) */
+int am_gemm_variant(const am_handle *h, int *split_digits);
+
 /* roofline denominator measured on the spot: TFLOP/s of a register-resident DFMA loop that fills
  * every SM of the current device (the same probe as tools/fp64_peak.cu). <= 0 on error. */
 double am_fp64_peak_tflops(void);

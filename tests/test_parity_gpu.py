@@ -37,9 +37,11 @@ def test_region_set_and_loops_match_oracle(oracle_lib, name):
 
 
 @pytest.mark.parametrize("name", ["chair_cube", "skipnet", "mlp4x128s"])
-def test_planes_bit_exact_with_oracle(oracle_lib, name):
-    """The composition kernels use the oracle's summation order: planes must match bit for bit."""
+def test_planes_bit_exact_with_oracle(oracle_lib, name, monkeypatch):
+    """The FP64 DMMA composition kernel uses the oracle's summation order: planes must match bit for bit
+    (the tcgen05 split-integer path has its own bit-exact restatement, tests/test_split_gpu.py)."""
     from analyticmesh_b200 import cuam
+    monkeypatch.setenv("AM_B200_GEMM_VARIANT", "0")
     case = build_case(name)
     info = case["info"]
     cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table, num_extra_constraints=0)
