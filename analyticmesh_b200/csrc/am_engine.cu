@@ -209,6 +209,38 @@ struct NcclApi {
     }
 };
 
+// Pinned host array that only grows: device->host copies of the mesh run at PCIe speed instead of being
+// staged through pageable memory, and a repeated am_combine pays neither allocation nor page faults.
+template <typename T>
+struct HostBuf {
+    T *p = nullptr;
+    size_t cap = 0, n = 0;
+    void resize(size_t want)
+    {
+        if (want > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            const size_t ncap = std::max<size_t>(want + want / 8, 1024);
+            CK(cudaMallocHost((void **)&p, ncap * sizeof(T)));
+            cap = ncap;
+        }
+        n = want;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = n = 0;
+    }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
+
 // ---- tcgen05 split-integer composition (split.cuh): tensor maps + weight digits --------------------------
 struct TmaApi {
     decltype(&cuTensorMapEncodeTiled) encode = nullptr;
@@ -320,6 +352,7 @@ struct am_handle {
     // ---- scratch ----
     DevBuf planes, equ, f_cnt, f_off, f_edges, f_verts, cand_slot, nwin, wbase, scan_a, scan_b, counters;
     DevBuf xkeys, xh, xpt, xslot, xstates;
+    DevBuf cmb_owner, cmb_flag, cmb_vid, cmb_cvid, cmb_verts;   // am_combine scratch, kept between calls
     // incremental composition: plane rows of the previous and the current level stay resident
     DevBuf lvl_planes[2], bucket, perm, bcounts;
     bool prev_resident = false;
@@ -333,6 +366,7 @@ struct am_handle {
     // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
     int gemm_variant = 0;                       // 0/1: FP64 DMMA tiles, 2: tcgen05 int8 split (split.cuh)
     int split_digits = 7;
+    int clip_minb = 3;                          // clip kernel variant: 3 = 3 CTAs/SM (measured best: 0.65 s vs 0.71 s with 2 at 8x512)
     int num_sms = 148;
     std::vector<SplitWeights> splitW, splitTM;  // index h = 1..D-1 / transform index
     DevBuf bdig, bscale;                        // plane digits [SD][b_ncap][b_pitch] and column scales of the current launch
@@ -361,9 +395,9 @@ struct am_handle {
     // ---- results ----
     bool has_march = false, has_mesh = false;
     am_stats stats{};
-    std::vector<double> h_vertices;
-    std::vector<int> h_corner_vid;
-    std::vector<long long> h_face_off;
+    HostBuf<double> h_vertices;
+    HostBuf<int> h_corner_vid;
+    HostBuf<long long> h_face_off;
     double gemm_ms = 0.0, gemm_flops = 0.0;
     long long gemm_launches = 0;
     // span kinds: 0 composition chain of a chunk, 1 compose phase, 2 clip, 3 frontier, 4 tensor GEMM kernel, 5 digit kernel
@@ -408,7 +442,7 @@ struct am_handle {
         DevBuf *all[] = {&P1, &wout, &extra, &keys, &hsum, &parent, &via, &seedpt, &face_off, &face_edges, &face_xyz,
                          &table, &planes, &equ, &f_cnt, &f_off, &f_edges, &f_verts, &cand_slot, &nwin, &wbase, &scan_a,
                          &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates, &lvl_planes[0], &lvl_planes[1],
-                         &bucket, &perm, &bcounts, &owner, &xchg};
+                         &bucket, &perm, &bcounts, &owner, &xchg, &cmb_owner, &cmb_flag, &cmb_vid, &cmb_cvid, &cmb_verts};
         for (DevBuf *b : all) b->release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear();
@@ -420,6 +454,7 @@ struct am_handle {
             join_event[c] = nullptr;
             chain_stream[c] = nullptr;
         }
+        h_vertices.release(); h_corner_vid.release(); h_face_off.release();
         if (h_counters) cudaFreeHost(h_counters);
         h_counters = nullptr;
         if (h_npre) cudaFreeHost(h_npre);
@@ -562,7 +597,12 @@ struct am_handle {
         const bool t = timing_on() && n_chain == 1;      // per-kernel events (the roofline of the dominant kernel)
         size_t e0 = 0;
         if (t) e0 = span_begin();
-        slice_rows_kernel<SD><<<(unsigned)((Sc + 7) / 8), 256, 0, cs>>>(sa);
+        if (w.Kpad <= 256)
+            slice_rows_reg_kernel<SD, 2><<<(unsigned)((Sc + 3) / 4), 128, 0, cs>>>(sa);
+        else if (w.Kpad <= 512)
+            slice_rows_reg_kernel<SD, 4><<<(unsigned)((Sc + 3) / 4), 128, 0, cs>>>(sa);
+        else
+            slice_rows_kernel<SD><<<(unsigned)((Sc + 7) / 8), 256, 0, cs>>>(sa);
         ++stats.n_launches;
         if (t) span_end(e0, 5, 0.0);
         SplitArgs g{};
@@ -980,7 +1020,14 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     ca.idx = idx;
     ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
     ca.counters = h->counters.as<unsigned long long>();
-    clip_kernel<<<(n + CLIP_WARPS - 1) / CLIP_WARPS, CLIP_WARPS * 32, CLIP_RING_BYTES, st>>>(ca);
+    const unsigned cgrid = (unsigned)((n + CLIP_WARPS - 1) / CLIP_WARPS);
+    switch (h->clip_minb) {   // AM_B200_CLIP_MINB: tuning knob (resident CTAs per SM / rows per lane / ring depth)
+        case 3: clip_kernel<3, 2, 3><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 3), st>>>(ca); break;
+        case 4: clip_kernel<2, 2, 4><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 4), st>>>(ca); break;
+        case 5: clip_kernel<2, 2, 5><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 5), st>>>(ca); break;
+        case 6: clip_kernel<2, 1, 6><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(1, 6), st>>>(ca); break;
+        default: clip_kernel<2, 2, 3><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 3), st>>>(ca); break;
+    }
     ++h->stats.n_launches;
     CK(cudaGetLastError());
 }
@@ -1269,7 +1316,7 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         }
         for (DevBuf *b : {&h->keys, &h->hsum, &h->parent, &h->via, &h->seedpt, &h->face_off, &h->owner, &h->face_edges,
                           &h->face_xyz, &h->lvl_planes[0], &h->lvl_planes[1], &h->xchg, &h->cand_slot, &h->f_verts,
-                          &h->planes, &h->table})
+                          &h->planes, &h->table, &h->cmb_owner, &h->cmb_flag, &h->cmb_vid, &h->cmb_cvid, &h->cmb_verts})
             b->vm = true;
         h->Wt.resize(h->D + 1); h->bias.resize(h->D + 1);
         h->Mpad.assign(h->D + 1, 0); h->Kpad.assign(h->D + 1, 0);
@@ -1287,7 +1334,12 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         CK(cudaMallocHost(&h->h_next, (size_t)(h->D + 3) * 4));
         h->next_counts.reserve((size_t)(h->D + 3) * 4);
         if (const char *e = getenv("AM_B200_INCREMENTAL")) h->incremental = atoi(e) != 0;
-        CK(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLIP_RING_BYTES));
+        CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
+        CK(cudaFuncSetAttribute(clip_kernel<3, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
+        CK(cudaFuncSetAttribute(clip_kernel<2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 4)));
+        CK(cudaFuncSetAttribute(clip_kernel<2, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 5)));
+        CK(cudaFuncSetAttribute(clip_kernel<2, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(1, 6)));
+        if (const char *e = getenv("AM_B200_CLIP_MINB")) h->clip_minb = atoi(e);
         h->counters.reserve(CNT_NUM * 8);
         {
             int kmax = 3;
@@ -1523,11 +1575,12 @@ int am_combine(am_handle *h, double scale, const double center[3])
         cudaStream_t st = h->stream;
         const long long nC = h->stats.n_corners;
         const long long nS = h->n_states;
-        DevBuf owner, flag, vid, cvid, verts;
-        h->h_face_off.assign((size_t)nS + 1, 0);
+        DevBuf &owner = h->cmb_owner, &flag = h->cmb_flag, &vid = h->cmb_vid, &cvid = h->cmb_cvid, &verts = h->cmb_verts;
+        h->h_face_off.resize((size_t)nS + 1);
+        h->h_face_off[0] = 0;
         if (nS) CK(cudaMemcpyAsync(h->h_face_off.data(), h->face_off.p, (size_t)(nS + 1) * 8, cudaMemcpyDeviceToHost, st));
-        h->h_vertices.clear();
-        h->h_corner_vid.assign((size_t)nC, 0);
+        h->h_vertices.resize(0);
+        h->h_corner_vid.resize((size_t)nC);
         unsigned long long *cnt = h->counters.as<unsigned long long>();
         long long nV = 0;
         if (nC > 0) {
@@ -1564,7 +1617,6 @@ int am_combine(am_handle *h, double scale, const double center[3])
         h->read_counters();
         h->stats.n_vertices = nV;
         h->stats.n_stitch_miss = (int64_t)h->h_counters[CNT_STITCH_MISS];
-        owner.release(); flag.release(); vid.release(); cvid.release(); verts.release();
         h->has_mesh = true;
     } catch (const CudaFail &f) {
         h->err = "am_combine: " + f.msg;

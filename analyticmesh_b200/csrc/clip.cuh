@@ -4,7 +4,7 @@
 // (backend/inc/process.h:208-321, inc/kernel.h:799-1385): there a host loop launches ~10 kernels
 // and does 4 blocking scalar copies per pivot step; here one warp owns one state and clips the
 // zero-level plane of the region's affine function against all C half-spaces in ONE pass over the
-// plane rows (each row is read exactly once, 32 rows per warp iteration, coalesced 1 KiB loads):
+// plane rows (each row is read exactly once, 64 rows per warp iteration, coalesced 1 KiB loads):
 //
 //   lane = plane:  d = sigma (a . v_j + c) for the <= 32 current vertices (broadcast from shared
 //                  memory); a plane "cuts" if some vertex has d * rsqrt(|a|^2) > EPS -- the
@@ -65,8 +65,8 @@ __device__ __forceinline__ void solve3(const double *r0, const double *r1, const
 }
 
 constexpr int CLIP_WARPS = 8;
-constexpr int CLIP_DEPTH = 4;     // cp.async ring: rows of the next CLIP_DEPTH-1 iterations are in flight per lane
-constexpr size_t CLIP_RING_BYTES = size_t(CLIP_WARPS) * CLIP_DEPTH * 32 * 4 * sizeof(double);
+constexpr int CLIP_KEY_WORDS = 128;   // key words kept in shared memory (L <= 4096)
+constexpr size_t clip_ring_bytes(int rpl, int depth) { return size_t(CLIP_WARPS) * depth * rpl * 32 * 4 * sizeof(double); }
 
 __device__ __forceinline__ void clip_cp16(void *smem, const void *gmem)
 {
@@ -74,13 +74,15 @@ __device__ __forceinline__ void clip_cp16(void *smem, const void *gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 
-__global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs a)
+template <int MINB, int RPL, int DEPTH>
+__global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipArgs a)
 {
-    extern __shared__ __align__(16) double s_ring[];  // [warp][CLIP_DEPTH][32 lanes][4]: plane rows in flight
+    extern __shared__ __align__(16) double s_ring[];  // [warp][DEPTH][RPL][32 lanes][4]: plane rows in flight
     __shared__ double s_pl[CLIP_WARPS][VSLOTS][4];   // plane of every polygon edge
     __shared__ __align__(16) double s_vx[CLIP_WARPS][VSLOTS + 4][4];   // vertex j = edge j ^ edge j+1 (x, y, z, -);
                                                      // slots k..k+3 repeat vertex 0 (unguarded 4-way loop)
     __shared__ int s_ed[CLIP_WARPS][VSLOTS];
+    __shared__ uint32_t s_key[CLIP_WARPS][CLIP_KEY_WORDS];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int slot = blockIdx.x * CLIP_WARPS + wib;
@@ -92,11 +94,11 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
     const unsigned FULL = 0xFFFFFFFFu;
 
     const uint32_t *key = a.keys + (size_t)s * a.kw;
-    // the key lives in registers: lane l holds words l, l+32, l+64, l+96 (L <= 4096); the word of a
-    // 32-row block is fetched with one shuffle instead of a dependent global load per iteration
+    // the key goes to shared memory once (first CLIP_KEY_WORDS words; longer keys read the rest from global)
     const int kwords = (a.L + 31) >> 5;
-    uint32_t kreg0 = (lane < kwords) ? key[lane] : 0u, kreg1 = (lane + 32 < kwords) ? key[lane + 32] : 0u;
-    uint32_t kreg2 = (lane + 64 < kwords) ? key[lane + 64] : 0u, kreg3 = (lane + 96 < kwords) ? key[lane + 96] : 0u;
+    uint32_t *skey = s_key[wib];
+    for (int w = lane; w < CLIP_KEY_WORDS; w += 32) skey[w] = (w < kwords) ? key[w] : 0u;
+    __syncwarp();
     double eq[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) eq[j] = a.equ[(size_t)s * 4 + j];
@@ -112,7 +114,6 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
     int k = 0;
     int n_inconsistent = 0;
     bool overflow = false;
-    const int C = a.L + a.E;
     for (int attempt = 0;; ++attempt) {
     k = 0;
     overflow = false;
@@ -153,81 +154,20 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
     }
     __syncwarp();
 
-    // row of constraint c for this state (layer 1 rows are shared, extra constraints follow the neurons)
-    auto row_of = [&](int c) -> const double * {
-        return (c < a.n1) ? a.P1 + (size_t)c * 4
-             : (c < a.L)  ? a.P + (size_t)s * a.p_stride + (size_t)(c - a.n1) * 4
-                          : a.extra + (size_t)(c - a.L) * 4;
-    };
-    // Every lane streams its own row of each 32-row block through a private shared-memory ring with
-    // cp.async, so CLIP_DEPTH-1 loads per lane are in flight without holding registers.
-    double *ring = s_ring + ((size_t)wib * CLIP_DEPTH * 32 + lane) * 4;
-    auto fetch = [&](int blk) {          // rows of block `blk` -> ring slot blk % CLIP_DEPTH
-        const int c = blk * 32 + lane;
-        if (c < C) {
-            const double *r = row_of(c);
-            double *dst = ring + (size_t)(blk % CLIP_DEPTH) * 32 * 4;
-            clip_cp16(dst, r);
-            clip_cp16(dst + 2, r + 2);
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-#pragma unroll
-    for (int b = 0; b < CLIP_DEPTH - 1; ++b) fetch(b);
-    for (int base = 0; base < C && k > 0 && !overflow; base += 32) {
-        const int c = base + lane;
-        const int blk = base >> 5;
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(CLIP_DEPTH - 2));
-        const double *mine = ring + (size_t)(blk % CLIP_DEPTH) * 32 * 4;
-        const double2 lo = *reinterpret_cast<const double2 *>(mine);
-        const double2 hi = *reinterpret_cast<const double2 *>(mine + 2);
-        fetch(blk + CLIP_DEPTH - 1);
-        uint32_t kword;   // activation bits of rows base .. base+31 (warp-uniform source lane)
-        if (blk < 128) {
-            const uint32_t sel = (blk < 32) ? kreg0 : (blk < 64) ? kreg1 : (blk < 96) ? kreg2 : kreg3;
-            kword = __shfl_sync(FULL, sel, blk & 31);
-        } else {
-            kword = (blk < kwords) ? key[blk] : 0u;
-        }
-        double p[4] = {0, 0, 0, 0};
-        double rs = 0.0;
-        bool cuts = false;
-        if (c < C) {
-            // sign 1 - 2 bit applied as an XOR on the IEEE sign bit (exact, and off the FP64 pipe)
-            const int flipbit = (c < a.L) ? int((kword >> lane) & 1u) << 31 : 0;
-            p[0] = __hiloint2double(__double2hiint(lo.x) ^ flipbit, __double2loint(lo.x));
-            p[1] = __hiloint2double(__double2hiint(lo.y) ^ flipbit, __double2loint(lo.y));
-            p[2] = __hiloint2double(__double2hiint(hi.x) ^ flipbit, __double2loint(hi.x));
-            p[3] = __hiloint2double(__double2hiint(hi.y) ^ flipbit, __double2loint(hi.y));
-            // Fast filter: d_j * rs > EPS needs d_j > 0 (rs >= 0; NaN compares false either way), so a
-            // plane with no vertex on its positive side cannot cut.  Slots k..k+3 repeat vertex 0, so the
-            // loop runs unguarded in steps of four.
-            bool pos = false;
-            for (int j = 0; j < k; j += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double2 xy = *reinterpret_cast<const double2 *>(&vx[j + u][0]);
-                    const double z = vx[j + u][2];
-                    const double d = p[0] * xy.x + p[1] * xy.y + p[2] * z + p[3];
-                    pos |= (d > 0.0);
-                }
-            }
-            if (pos) {   // rare: evaluate the reference's predicate exactly
-                rs = rsqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-                for (int j = 0; j < k; ++j) {
-                    const double d = p[0] * vx[j][0] + p[1] * vx[j][1] + p[2] * vx[j][2] + p[3];
-                    cuts |= (d * rs > EPS_FEAS);
-                }
-            }
-        }
-        unsigned todo = __ballot_sync(FULL, cuts);
+    // Every lane streams its own two rows of each 64-row block through a private shared-memory ring with
+    // cp.async, so the rows of the next CLIP_DEPTH-1 blocks are in flight without holding registers.
+    double *ring = s_ring + (size_t)wib * DEPTH * (RPL * 32) * 4;
+    // applies the cutting planes of one 32-row half block, one at a time in row order (p, rs: this lane's row)
+    auto apply_cuts = [&](unsigned long long todo, const double (&p)[RPL][4], const double (&rs)[RPL], int ebase) {
         while (todo) {
-            const int src = __ffs(todo) - 1;
+            const int idx = __ffsll((long long)todo) - 1;          // bit 32 h + lane: row h of that lane, in row order
             todo &= todo - 1;
+            const int src = idx & 31;
+            const bool second = RPL > 1 && idx >= 32;
             double q[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) q[j] = __shfl_sync(FULL, p[j], src);
-            const double qrs = __shfl_sync(FULL, rs, src);
+            for (int j = 0; j < 4; ++j) q[j] = __shfl_sync(FULL, second ? p[RPL - 1][j] : p[0][j], src);
+            const double qrs = __shfl_sync(FULL, second ? rs[RPL - 1] : rs[0], src);
             bool out = false;
             if (lane < k) {
                 const double d = q[0] * vx[lane][0] + q[1] * vx[lane][1] + q[2] * vx[lane][2] + q[3];
@@ -258,7 +198,7 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
                 } else if (lane == 1) {   // (new plane, vertex = new plane ^ edge rb1)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) npl[j] = q[j];
-                    ned = base + src;
+                    ned = ebase + idx;
                     solve3(q, pl[rb1], eq, nvx);
                 } else {
                     const int o = (rb1 + lane - 2) % k;
@@ -284,6 +224,103 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, 3) clip_kernel(const ClipArgs
             }
             __syncwarp();
         }
+    };
+    // The constraints come in three contiguous row segments (layer-1 rows shared by all states, the
+    // state's own rows, the extra constraints); each segment is streamed in 64-row blocks with a running
+    // pointer, so the loop body carries no per-row address selection.
+    static_assert(RPL <= 2, "apply_cuts selects between at most two rows per lane");
+#pragma unroll 1
+    for (int seg = 0; seg < 3; ++seg) {
+        const double *rows0 = (seg == 0) ? a.P1 : (seg == 1) ? a.P + (size_t)s * a.p_stride : a.extra;
+        const int c0 = (seg == 0) ? 0 : (seg == 1) ? a.n1 : a.L;
+        const int nrows = (seg == 0) ? a.n1 : (seg == 1) ? a.L - a.n1 : a.E;
+        const bool has_bits = seg < 2;
+        if (nrows <= 0 || k <= 0 || overflow) continue;
+        constexpr int BR = RPL * 32;                 // rows per block
+        const int nblk = (nrows + BR - 1) / BR;
+        // a block is BR * 32 contiguous bytes: copy instruction i moves its 16-byte pieces 32 i .. 32 i + 31
+        // (fully coalesced 512 B), whichever rows they belong to; the rows are read back after a warp sync
+        const double *src = rows0 + (size_t)lane * 2;
+        auto fetch = [&](int b) {            // rows BR b .. BR b + BR - 1 -> ring slot b % DEPTH
+            double *dst = ring + (size_t)(b % DEPTH) * (BR * 4) + lane * 2;
+            const double *r = src + (size_t)b * (BR * 4);
+            const int row0 = b * BR + (lane >> 1);
+#pragma unroll
+            for (int i = 0; i < 2 * RPL; ++i)
+                if (row0 + 16 * i < nrows) clip_cp16(dst + i * 64, r + i * 64);
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
+#pragma unroll
+        for (int b = 0; b < DEPTH - 1; ++b) fetch(b);
+        for (int b = 0; b < nblk && k > 0 && !overflow; ++b) {
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(DEPTH - 2));
+            __syncwarp();                            // the pieces of this lane's rows were copied by other lanes
+            const double *mine = ring + (size_t)(b % DEPTH) * (BR * 4) + lane * 4;
+            double2 lo[RPL], hi[RPL];
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) {
+                lo[h] = *reinterpret_cast<const double2 *>(mine + h * 128);
+                hi[h] = *reinterpret_cast<const double2 *>(mine + h * 128 + 2);
+            }
+            fetch(b + DEPTH - 1);
+            double p[RPL][4];
+            double rs[RPL];
+            bool cuts[RPL], pos[RPL];
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) {
+                rs[h] = 0.0;
+                cuts[h] = pos[h] = false;
+                const int r = b * BR + h * 32 + lane;
+                const int c = c0 + r;
+                // sign 1 - 2 bit applied as an XOR on the IEEE sign bit (exact, and off the FP64 pipe); rows
+                // past the end of the segment are zero and never cut
+                int flipbit = 0;
+                if (has_bits) {
+                    const uint32_t w = ((c >> 5) < CLIP_KEY_WORDS) ? skey[c >> 5] : key[c >> 5];
+                    flipbit = int((w >> (c & 31)) & 1u) << 31;
+                }
+                const bool live = r < nrows;
+                p[h][0] = live ? __hiloint2double(__double2hiint(lo[h].x) ^ flipbit, __double2loint(lo[h].x)) : 0.0;
+                p[h][1] = live ? __hiloint2double(__double2hiint(lo[h].y) ^ flipbit, __double2loint(lo[h].y)) : 0.0;
+                p[h][2] = live ? __hiloint2double(__double2hiint(hi[h].x) ^ flipbit, __double2loint(hi[h].x)) : 0.0;
+                p[h][3] = live ? __hiloint2double(__double2hiint(hi[h].y) ^ flipbit, __double2loint(hi[h].y)) : 0.0;
+            }
+            // Fast filter: d_j * rs > EPS needs d_j > 0 (rs >= 0; NaN compares false either way), so a plane
+            // with no vertex on its positive side cannot cut.  Slots k..k+3 repeat vertex 0, so the loop runs
+            // unguarded in steps of four; every vertex load serves both rows of the lane.
+            for (int j = 0; j < k; j += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double2 xy = *reinterpret_cast<const double2 *>(&vx[j + u][0]);
+                    const double z = vx[j + u][2];
+#pragma unroll
+                    for (int h = 0; h < RPL; ++h) {
+                        const double d = p[h][0] * xy.x + p[h][1] * xy.y + p[h][2] * z + p[h][3];
+                        pos[h] |= (d > 0.0);
+                    }
+                }
+            }
+            bool any_pos = false;
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) any_pos |= pos[h];
+            if (!__any_sync(FULL, any_pos)) continue;                   // the common case: nothing near the polygon
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) {
+                if (pos[h]) {   // rare: evaluate the reference's predicate exactly
+                    rs[h] = rsqrt(p[h][0] * p[h][0] + p[h][1] * p[h][1] + p[h][2] * p[h][2]);
+                    for (int j = 0; j < k; ++j) {
+                        const double d = p[h][0] * vx[j][0] + p[h][1] * vx[j][1] + p[h][2] * vx[j][2] + p[h][3];
+                        cuts[h] |= (d * rs[h] > EPS_FEAS);
+                    }
+                }
+            }
+            unsigned long long todo = 0ull;
+#pragma unroll
+            for (int h = 0; h < RPL; ++h) todo |= (unsigned long long)__ballot_sync(FULL, cuts[h]) << (32 * h);
+            if (todo) apply_cuts(todo, p, rs, c0 + b * BR);
+        }
+        asm volatile("cp.async.wait_all;\n" ::);   // drain before the next segment reuses the ring
+        __syncwarp();
     }
 
     asm volatile("cp.async.wait_all;\n" ::);   // the loop may leave early with copies still in flight

@@ -144,6 +144,75 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a)
     }
 }
 
+// Same result, one pass: for K <= 128 NIT the lane keeps its rows in registers between the column
+// maximum and the digit extraction (every load is issued up front, nothing is read twice).
+template <int SD, int NIT>
+__global__ void __launch_bounds__(128) slice_rows_reg_kernel(const SliceArgs a)
+{
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= a.S || (slot / SP_BS) % a.tile_stride != a.tile_offset) return;
+    const int s = a.perm ? a.perm[slot] : slot;
+    const double *rows = a.src + (size_t)s * a.stride;
+    const uint32_t *key = a.keys + (size_t)s * a.kw;
+
+    double v[NIT][4][4];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int k0 = it * 128 + lane * 4;
+        uint32_t bits = 0;
+        if (k0 < a.K) {
+            const int bit = a.bit0 + k0, w = bit >> 5;
+            const uint32_t w0 = key[w], w1 = (w + 1 < a.kw) ? key[w + 1] : 0u;
+            bits = __funnelshift_r(w0, w1, bit & 31);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
+            if (k0 + j < a.K && ((bits >> j) & 1u)) {
+                p = *reinterpret_cast<const double2 *>(rows + (size_t)(k0 + j) * 4);
+                q = *reinterpret_cast<const double2 *>(rows + (size_t)(k0 + j) * 4 + 2);
+            }
+            v[it][j][0] = p.x; v[it][j][1] = p.y; v[it][j][2] = q.x; v[it][j][3] = q.y;
+        }
+    }
+    double mul[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double mx = 0.0;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mx = fmax(mx, fabs(v[it][j][c]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int e = 0;
+        if (mx > 0.0 && mx < 1.7e308) frexp(mx, &e);
+        mul[c] = ldexp(1.0, SplitCfg<SD>::FRAC_BITS - e);
+        if (lane == 0) a.scale[(size_t)slot * 4 + c] = ldexp(1.0, e - 6);
+    }
+    signed char *col0 = a.dig + (size_t)slot * 4 * a.pitch;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int k0 = it * 128 + lane * 4;
+        if (k0 >= a.Kpad) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            unsigned long long Y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Y[j] = split_pack(__double2ll_rn(v[it][j][c] * mul[c]), SD);
+#pragma unroll
+            for (int t = 0; t < SD; ++t) {
+                const int p = SD - 1 - t;
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w |= (uint32_t)((Y[j] >> (8 * p)) & 0xFFull) << (8 * j);
+                *reinterpret_cast<uint32_t *>(col0 + (size_t)t * a.slice_stride + (size_t)c * a.pitch + k0) = w;
+            }
+        }
+    }
+}
+
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -273,12 +273,17 @@ def main():
     e0.record()
     e_faces = 0
     d2h = 0
+    e2e_parts = {"march_host_buffers": 0.0, "combine_and_read_back": 0.0}
     for _ in range(args.steps):
+        t0 = time.time()
         st = march(host)
+        t1 = time.time()
         if rank == 0:   # the mesh is replicated: one rank stitches it and reads it back
             cuam.CombineMesh(scale=1.0, center=[0.0, 0.0, 0.0])
             st = cuam.stats()
             d2h = st["n_vertices"] * 24 + st["n_corners"] * 4 + (st["n_states"] + 1) * 8
+        e2e_parts["march_host_buffers"] += (t1 - t0) / args.steps
+        e2e_parts["combine_and_read_back"] += (time.time() - t1) / args.steps
         e_faces += st["n_faces"]
     e1.record()
     barrier()
@@ -326,6 +331,7 @@ def main():
                                        "am_time": dt / args.steps, "am_plus_combine_host_buffers": e_dt / args.steps,
                                        "export_time": export_time, "ply_bytes": ply_bytes},
                        "engine_stream_seconds_per_step": engine_s / args.steps,
+                       "e2e_wall_seconds_per_step_rank0": e2e_parts,
                        "phase_seconds_last_step_rank0": phases,
                        "algorithmic_flops_per_face": fpf,
                        "arithmetic": (f"FP64 planes; contraction as {split_digits} x {split_digits} signed 8-bit digit planes on "
