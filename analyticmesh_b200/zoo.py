@@ -83,3 +83,24 @@ def by_name(name):
         d, w = (int(x) for x in spec.rstrip("s").split("x"))
         return sal(depth=d, width=w, skip=skip)
     raise ValueError(name)
+
+
+def latent_shapes(model, n_shapes, latent_dim=256, sigma=0.01, seed=0):
+    """BASELINE.json config 5: a DeepSDF-style decoder whose first layer sees (x, latent code).  For a fixed code
+    c_k the latent columns W_c fold into the bias, b'_0 = W_c c_k + b_0 (reference README.md:181), so every
+    shape is a plain 3-input MLP that shares all weights with `model` except biases[0].
+    Returns the list of first-layer biases (float32 tensors), shape k drawn with torch.manual_seed(k)."""
+    lin0 = model.linears[0]
+    n1 = lin0.weight.shape[0]
+    g = torch.Generator().manual_seed(seed)
+    w_c = torch.randn(n1, latent_dim, generator=g) * (math.sqrt(2) / math.sqrt(n1))
+    out = []
+    for k in range(n_shapes):
+        c = torch.randn(latent_dim, generator=torch.Generator().manual_seed(k)) * sigma
+        out.append((w_c @ c + lin0.bias.detach().cpu().float()).contiguous())
+    return out
+
+
+def shapes_of_rank(n_shapes, rank, world):
+    """Replica sharding of a batch of shapes: shape k runs on GPU k mod world, no collective."""
+    return [k for k in range(n_shapes) if k % world == rank]

@@ -74,3 +74,39 @@ def test_pybind_module_matches_ctypes_binding(tmp_path):
     with pytest.raises(RuntimeError):
         pyb.Init(float_type="float64", nodesnum=[2, 5, 1], arc_table=torch.zeros(1, 1, dtype=torch.int32),
                  num_extra_constraints=0)
+
+
+def test_batch_of_latent_shapes_reuses_the_environment(oracle_lib):
+    """BASELINE.json config 5 in small: shapes that share every weight but biases[0] are marched one after the
+    other in ONE environment; each equals the oracle on its own network."""
+    import random
+    import torch
+    from analyticmesh_b200 import zoo, cuam
+    from analyticmesh_b200.netinfo import NetInfo
+    from analyticmesh_b200.initializers import dichotomy, states_of
+    from tests import parity
+    model = zoo.sal(depth=3, width=32, skip=False, seed=1)
+    biases0 = zoo.latent_shapes(model, 3, latent_dim=16, sigma=0.05)
+    assert zoo.shapes_of_rank(7, 1, 3) == [1, 4] and sorted(sum((zoo.shapes_of_rank(7, r, 3) for r in range(3)), [])) == list(range(7))
+    counts = []
+    for k, b0 in enumerate(biases0):
+        with torch.no_grad():
+            model.linears[0].bias.copy_(b0)
+        pts = dichotomy(model, 0.0, 64, generator=torch.Generator().manual_seed(k), rng=random.Random(k))
+        info = NetInfo.from_model(model)
+        case = dict(info=info, states=states_of(model, pts).numpy(), points=pts.double().numpy(),
+                    w_extra=np.zeros((0, 3)), b_extra=np.zeros(0))
+        if k == 0:
+            eng = parity.run_engine(case, combine=False)          # Init happens here, once
+        else:
+            cuam.AnalyticMarching(weights=info.weights, biases=info.biases, states=case["states"], points=case["points"],
+                                  arc_tm=info.arc_tm, w_extra_constraints=np.zeros((0, 3)),
+                                  b_extra_constraints=np.zeros(0), iso=0.0, flip_insideout=False)
+            keys, face_off, parent, via = cuam.states()
+            edges, xyz = cuam.faces()
+            eng = dict(keys=keys, face_off=face_off, parent=parent, via=via, edges=edges, xyz=xyz, stats=cuam.stats())
+        orc = oracle_lib.march(info, case["states"], case["points"], None, None)
+        rep = parity.compare_with_oracle(eng, orc, info.state_len)
+        assert rep["keys_equal"] and rep["loops_equal"] and rep["max_vertex_err"] < 1e-9, (k, rep)
+        counts.append(eng["stats"]["n_faces"])
+    assert len(set(counts)) > 1 or counts[0] > 0

@@ -298,3 +298,35 @@ def test_polymesh_roundtrip_and_poly2tri(tmp_path):
     assert o.faces() == faces and np.allclose(o.vertices(), verts)
     with pytest.raises(RuntimeError):
         PolyMesh(str(tmp_path / "x.stl"))
+
+
+# ---------------------------------------------------------------- split-integer restatement ------
+def test_split_digits_reconstruct_exactly():
+    """tests/split_emul.py (the CPU restatement of csrc/split.cuh): digits are int8 and rebuild the scaled integer."""
+    from tests import split_emul
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((5, 64)) * np.exp(rng.uniform(-20, 20, (5, 1)))
+    x[1, 3] = 0.0
+    for sd in (6, 7, 8):
+        e = split_emul._exponent(np.abs(x).max(axis=1))[:, None]
+        d = split_emul.digits(x, e, sd)
+        assert d.min() >= -128 and d.max() <= 127
+        X = sum(d[t].astype(object) * (256 ** (sd - 1 - t)) for t in range(sd))
+        want = np.rint(np.ldexp(x, (8 * sd - 2) - e)).astype(np.int64).astype(object)
+        assert (X == want).all()
+        back = np.ldexp(np.array(X, dtype=np.float64), e - (8 * sd - 2))
+        assert np.abs(back - x).max() <= np.ldexp(np.abs(x).max(axis=1), -(8 * sd - 3)).max()
+
+
+def test_split_gemm_restatement_matches_fp64_reference(oracle_lib):
+    """The split-integer composition agrees with the FMA-chain oracle to a few ulp of the column maximum."""
+    from tests import split_emul
+    from tests.golden.cases import build_case
+    case = build_case("skipnet")
+    info = case["info"]
+    for i in range(3):
+        p, _ = oracle_lib.compose(info, case["states"][i], iso=0.0)
+        q = split_emul.compose(info, case["states"][i], 7)
+        scale = np.abs(p).max(axis=0)
+        scale[scale == 0] = 1.0
+        assert (np.abs(p - q) / scale).max() < 1e-14
