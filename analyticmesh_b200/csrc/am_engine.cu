@@ -366,6 +366,8 @@ struct am_handle {
     // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
     int gemm_variant = 0;                       // 0/1: FP64 DMMA tiles, 2: tcgen05 int8 split (split.cuh)
     int split_digits = 7;
+    const double *fused_add_in = nullptr;       // input skip of the layer being launched, applied in the GEMM epilogue
+    int fused_add_identity = 0;
     int clip_minb = 3;                          // clip kernel variant: 3 = 3 CTAs/SM (measured best: 0.65 s vs 0.71 s with 2 at 8x512)
     int num_sms = 148;
     std::vector<SplitWeights> splitW, splitTM;  // index h = 1..D-1 / transform index
@@ -609,6 +611,8 @@ struct am_handle {
         g.k_steps = w.Kpad / SP_BK; g.M = M; g.m_tiles = w.Mpad / SP_BM; g.S = Sc; g.perm = perm_;
         g.out = out; g.out_stride = 4LL * R; g.bias = bias_; g.scaleA = w.scale.as<double>();
         g.scaleB = bscale.as<double>(); g.accumulate = accumulate; g.tile_stride = n_chain; g.tile_offset = chain;
+        g.add_in = accumulate ? nullptr : fused_add_in;
+        g.add_identity = accumulate ? 0 : fused_add_identity;
         g.n_tiles = g.m_tiles * mine;
         if (t) e0 = span_begin();
         split_gemm_kernel<SD><<<(unsigned)std::min(g.n_tiles, num_sms), SP_THREADS, SplitCfg<SD>::SMEM, cs>>>(
@@ -687,11 +691,22 @@ struct am_handle {
             double *out = base + 4LL * (off[h + 1] - n1);
             const int Sc = npre ? npre[h] : S_all;
             if (Sc == 0) continue;                 // nobody needs this layer recomputed
+            // tcgen05 path: the first skip from the raw input is an addend of the GEMM epilogue (no extra pass)
+            const Skip *fused = nullptr;
+            fused_add_in = nullptr;
+            fused_add_identity = 0;
+            if (gemm_variant == 2 && !skips[h].empty() && skips[h][0].src == 0) {   // first in the list: order kept
+                const Skip &sk = skips[h][0];
+                fused = &sk;
+                if (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0) fused_add_identity = 1;
+                else fused_add_in = TM[sk.tm].as<double>();
+            }
             for (int c = 0; c < n_chain; ++c) {
                 cudaStream_t cs = (n_chain > 1) ? chain_stream[c] : stream;
                 launch_gemm(Wt[h].as<double>(), Mpad[h], n[h + 1], n[h], Bsrc, bstride, off[h], out,
                             bias[h].as<double>(), keys0, Sc, 0, prm, c, n_chain, gemm_variant == 2 ? &splitW[h] : nullptr);
                 for (const Skip &sk : skips[h]) {
+                    if (&sk == fused) continue;
                     const bool identity = (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0);
                     const int M = n[h + 1];
                     if (sk.src == 0) {

@@ -291,6 +291,8 @@ struct SplitArgs {
     const double *scaleB;       // [S * 4]  2^(eB - 6)
     int accumulate;             // out += result
     int tile_stride, tile_offset;
+    const double *add_in;       // fused skip connection from the raw input: out[m][0..2] += add_in[3 m + 0..2]
+    int add_identity;           //   ... or += I3 (identity skip: rows m < 3 get +1 on their own column)
 };
 
 // exact int32 -> double on the FP64 pipe (LOP3 + DADD; I2F.F64 runs at a quarter of that rate)
@@ -405,6 +407,10 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const bool m_ok = m < a.M;
             const double sA = m_ok ? a.scaleA[m] : 0.0;
             const double bias = (m_ok && a.bias != nullptr) ? a.bias[m] : 0.0;
+            double add[3] = {0.0, 0.0, 0.0};
+            if (m_ok && a.add_in != nullptr) { add[0] = a.add_in[3 * m]; add[1] = a.add_in[3 * m + 1]; add[2] = a.add_in[3 * m + 2]; }
+            if (m_ok && a.add_identity && m < 3) add[m] = 1.0;
+            const bool has_add = a.add_in != nullptr || a.add_identity;
             asm volatile("bar.sync 1, 128;\n" ::: "memory");
             mbar_wait(bar_tfull, tphase);
             tphase ^= 1u;
@@ -434,6 +440,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         r[c] = acc * sA * sb[c];
                     }
                     r[3] += bias;
+                    if (has_add) { r[0] += add[0]; r[1] += add[1]; r[2] += add[2]; }
                     double2 *dst = reinterpret_cast<double2 *>(a.out + (size_t)s * a.out_stride + (size_t)m * 4);
                     if (a.accumulate) {
                         const double2 o0 = dst[0], o1 = dst[1];
