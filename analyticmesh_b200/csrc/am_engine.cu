@@ -366,9 +366,13 @@ struct am_handle {
     // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
     int gemm_variant = 0;                       // 0/1: FP64 DMMA tiles, 2: tcgen05 int8 split (split.cuh)
     int split_digits = 7;
+    // read-through of the parent's rows instead of copy_parent_rows_kernel (tcgen05 path, no hidden-source skips)
+    bool lazy_ok = false;
+    const double *lazy_prev = nullptr;          // previous level's rows while a level is processed lazily, else nullptr
+    long long lazy_lb = 0, lazy_prev_lb = 0;
     const double *fused_add_in = nullptr;       // input skip of the layer being launched, applied in the GEMM epilogue
     int fused_add_identity = 0;
-    int clip_minb = 3;                          // clip kernel variant: 3 = 3 CTAs/SM (measured best: 0.65 s vs 0.71 s with 2 at 8x512)
+    int clip_minb = 2;                          // clip kernel variant (AM_B200_CLIP_MINB): 2 CTAs/SM, no spills; 3 = 3 CTAs/SM
     int num_sms = 148;
     std::vector<SplitWeights> splitW, splitTM;  // index h = 1..D-1 / transform index
     DevBuf bdig, bscale;                        // plane digits [SD][b_ncap][b_pitch] and column scales of the current launch
@@ -585,7 +589,7 @@ struct am_handle {
     template <int SD>
     bool launch_split(const SplitWeights &w, int M, int K, const double *Bsrc, long long bstride, int bit0, double *out,
                       const double *bias_, const uint32_t *keys0, int Sc, int accumulate, const int *perm_, int chain,
-                      int n_chain, cudaStream_t cs)
+                      int n_chain, cudaStream_t cs, int alt_from_slot, const double *alt_src)
     {
         const int tiles = (Sc + SP_BS - 1) / SP_BS;
         const int mine = (tiles - chain + n_chain - 1) / n_chain;
@@ -596,6 +600,8 @@ struct am_handle {
         sa.perm = perm_; sa.S = Sc; sa.dig = bdig.as<signed char>(); sa.pitch = (long long)b_pitch;
         sa.slice_stride = (long long)(b_ncap * b_pitch); sa.scale = bscale.as<double>();
         sa.tile_stride = n_chain; sa.tile_offset = chain;
+        sa.alt_from_slot = alt_from_slot; sa.alt_src = alt_src; sa.parent = parent.as<int>();
+        sa.lb = (int)lazy_lb; sa.prev_lb = (int)lazy_prev_lb;
         const bool t = timing_on() && n_chain == 1;      // per-kernel events (the roofline of the dominant kernel)
         size_t e0 = 0;
         if (t) e0 = span_begin();
@@ -623,7 +629,8 @@ struct am_handle {
 
     void launch_gemm(const double *Wt_, int Mpad_, int M, int K, const double *Bsrc, long long bstride, int bit0,
                      double *out, const double *bias_, const uint32_t *keys0, int Sc, int accumulate, const int *perm_,
-                     int chain = 0, int n_chain = 1, const SplitWeights *sw = nullptr)
+                     int chain = 0, int n_chain = 1, const SplitWeights *sw = nullptr, int alt_from_slot = 0x7fffffff,
+                     const double *alt_src = nullptr)
     {
         GemmArgs g{};
         g.Wt = Wt_; g.Mpad = Mpad_; g.M = M; g.K = K;
@@ -649,9 +656,9 @@ struct am_handle {
             case 2:
                 if (sw == nullptr) throw CudaFail{"split GEMM without weight digits"};
                 switch (split_digits) {
-                    case 6: launched = launch_split<6>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs); break;
-                    case 8: launched = launch_split<8>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs); break;
-                    default: launched = launch_split<7>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs); break;
+                    case 6: launched = launch_split<6>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs, alt_from_slot, alt_src); break;
+                    case 8: launched = launch_split<8>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs, alt_from_slot, alt_src); break;
+                    default: launched = launch_split<7>(*sw, M, K, Bsrc, bstride, bit0, out, bias_, keys0, Sc, accumulate, perm_, chain, n_chain, cs, alt_from_slot, alt_src); break;
                 }
                 break;
             default: go(GemmDefault{}); break;
@@ -703,8 +710,17 @@ struct am_handle {
             }
             for (int c = 0; c < n_chain; ++c) {
                 cudaStream_t cs = (n_chain > 1) ? chain_stream[c] : stream;
+                // read-through: the permutation slots [npre[h-1], npre[h]) flipped a neuron of layer h itself, the
+                // rows of layer h are their parent's
+                int alt_from = 0x7fffffff;
+                const double *alt_src = nullptr;
+                if (lazy_prev != nullptr && npre != nullptr && h >= 2) {
+                    alt_from = npre[h - 1];
+                    alt_src = lazy_prev + 4LL * (off[h] - n1);
+                }
                 launch_gemm(Wt[h].as<double>(), Mpad[h], n[h + 1], n[h], Bsrc, bstride, off[h], out,
-                            bias[h].as<double>(), keys0, Sc, 0, prm, c, n_chain, gemm_variant == 2 ? &splitW[h] : nullptr);
+                            bias[h].as<double>(), keys0, Sc, 0, prm, c, n_chain, gemm_variant == 2 ? &splitW[h] : nullptr,
+                            alt_from, alt_src);
                 for (const Skip &sk : skips[h]) {
                     if (&sk == fused) continue;
                     const bool identity = (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0);
@@ -749,6 +765,12 @@ struct am_handle {
         e.idx = equ_idx;
         e.keys = keys0; e.kw = kw; e.bit0 = off[D]; e.K = n[D]; e.S = Sc;
         e.equ = equ.as<double>();
+        e.bucket = nullptr;
+        if (lazy_prev != nullptr && D >= 2) {
+            e.bucket = bucket.as<int>(); e.parent = parent.as<int>();
+            e.lb = (int)lazy_lb; e.prev_lb = (int)lazy_prev_lb; e.D = D;
+            e.alt_in = lazy_prev + 4LL * (off[D] - n1);
+        }
         e.n_skips = 0;
         for (const Skip &sk : skips[D]) {
             if (e.n_skips == EQU_MAX_SKIPS) throw CudaFail{"more than 4 skips into the output layer"};
@@ -1033,6 +1055,12 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     ca.L = h->L; ca.E = h->E; ca.S = n; ca.flip = flip;
     ca.seedpt = h->seedpt.as<double>() + (size_t)sid0 * 4;
     ca.idx = idx;
+    ca.P_prev = h->lazy_prev;
+    ca.P_own = const_cast<double *>(planes_base);
+    ca.bucket = h->bucket.as<int>(); ca.parent = h->parent.as<int>();
+    ca.lb = (int)h->lazy_lb; ca.prev_lb = (int)h->lazy_prev_lb;
+    ca.lo.D = h->D;
+    for (int l = 1; l <= h->D + 1; ++l) ca.lo.off[l] = h->off[l];
     ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
     ca.counters = h->counters.as<unsigned long long>();
     const unsigned cgrid = (unsigned)((n + CLIP_WARPS - 1) / CLIP_WARPS);
@@ -1159,7 +1187,12 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         }
         if (!have) CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 2) * 4, cudaMemcpyDeviceToHost, st));
         if (sharded) CK(cudaMemsetAsync(sc.cnt, 0, (size_t)S * 4, st));   // counts of states owned elsewhere
-        if (h->prev_resident) {
+        h->lazy_prev = nullptr;
+        if (h->prev_resident && h->lazy_ok) {        // no copy: slice / level-plane / clip kernels read the parent's rows
+            h->lazy_prev = h->lvl_planes[h->prev_buf].as<double>();
+            h->lazy_lb = lb;
+            h->lazy_prev_lb = h->prev_lb;
+        } else if (h->prev_resident) {
             copy_parent_rows_kernel<<<(unsigned)((S + 7) / 8), 256, 0, st>>>(
                 h->bucket.as<int>(), h->parent.as<int>(), (int)lb, (int)S, (int)h->prev_lb,
                 h->lvl_planes[h->prev_buf].as<double>(), base, 4LL * h->R, lo, h->n1);
@@ -1178,6 +1211,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         if (timing) t0 = h->span_begin();
         run_clip(h, lb, sharded ? n_mine : (int)S, base, flip, sharded ? h->perm.as<int>() : nullptr, sc);
         store_faces(h, lb, (int)S, sc);   // sharded: + the level's collectives (sizes, edges, vertices)
+        h->lazy_prev = nullptr;
         if (timing) h->span_end(t0, 2);
         h->prev_resident = true;
         h->prev_buf = cur;
@@ -1368,6 +1402,13 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             };
             if (const char *e = getenv("AM_B200_SPLIT_DIGITS")) h->split_digits = std::max(6, std::min(8, atoi(e)));
+            // read-through of the parent's rows: the consumers that know how are the tcgen05 digit kernels, the
+            // level-plane kernel and the clip kernel; skips that read a hidden layer keep the copy kernel
+            h->lazy_ok = (h->gemm_variant == 2);
+            for (int l = 1; l <= h->D; ++l)
+                for (const Skip &sk : h->skips[l])
+                    if (sk.src >= 1) h->lazy_ok = false;
+            if (const char *e = getenv("AM_B200_READ_THROUGH")) h->lazy_ok = h->lazy_ok && atoi(e) != 0;
             h->splitW.resize(h->D + 1);
             {
                 int dev = 0;

@@ -40,6 +40,14 @@ struct ClipArgs {
     int L, E, S, flip;
     const double *seedpt;     // [S][4] seed point (x, y, z) and size hint (0 = none) of state 0 of the chunk
     const int *idx;           // optional list of the states to process (sharded mode); S = its length
+    // read-through: rows of layers 2..bucket are read from the parent's level buffer and written to the
+    // state's own buffer on the way (they replace copy_parent_rows_kernel); nullptr = everything is own
+    const double *P_prev;     // [S_prev][R][4]
+    double *P_own;            // = P, writable
+    const int *bucket;        // per state of the level
+    const int *parent;        // indexed by global state id
+    int lb, prev_lb;
+    LayerOffs lo;
     int *out_cnt;             // [S]
     int *out_edges;           // [S][VSLOTS]
     double *out_verts;        // [S][VSLOTS][3]
@@ -229,12 +237,24 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
     // state's own rows, the extra constraints); each segment is streamed in 64-row blocks with a running
     // pointer, so the loop body carries no per-row address selection.
     static_assert(RPL <= 2, "apply_cuts selects between at most two rows per lane");
+    // rows inherited from the parent (layers 2..bucket): read there, stored into the own buffer on the way
+    int inh = 0;
+    const double *inh_src = nullptr;
+    if (a.P_prev != nullptr) {
+        const int bkt = a.bucket[s];
+        if (bkt >= 2 && bkt <= a.lo.D) {
+            inh = a.lo.off[bkt + 1] - a.n1;
+            inh_src = a.P_prev + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.p_stride;
+        }
+    }
 #pragma unroll 1
-    for (int seg = 0; seg < 3; ++seg) {
-        const double *rows0 = (seg == 0) ? a.P1 : (seg == 1) ? a.P + (size_t)s * a.p_stride : a.extra;
-        const int c0 = (seg == 0) ? 0 : (seg == 1) ? a.n1 : a.L;
-        const int nrows = (seg == 0) ? a.n1 : (seg == 1) ? a.L - a.n1 : a.E;
-        const bool has_bits = seg < 2;
+    for (int seg = 0; seg < 4; ++seg) {
+        const double *own = a.P + (size_t)s * a.p_stride;
+        const double *rows0 = (seg == 0) ? a.P1 : (seg == 1) ? inh_src : (seg == 2) ? own + (size_t)inh * 4 : a.extra;
+        const int c0 = (seg == 0) ? 0 : (seg == 1) ? a.n1 : (seg == 2) ? a.n1 + inh : a.L;
+        const int nrows = (seg == 0) ? a.n1 : (seg == 1) ? inh : (seg == 2) ? a.L - a.n1 - inh : a.E;
+        const bool has_bits = seg < 3;
+        double *wr = (seg == 1) ? a.P_own + (size_t)s * a.p_stride + (size_t)lane * 2 : nullptr;
         if (nrows <= 0 || k <= 0 || overflow) continue;
         constexpr int BR = RPL * 32;                 // rows per block
         const int nblk = (nrows + BR - 1) / BR;
@@ -255,6 +275,15 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
         for (int b = 0; b < nblk && k > 0 && !overflow; ++b) {
             asm volatile("cp.async.wait_group %0;\n" ::"n"(DEPTH - 2));
             __syncwarp();                            // the pieces of this lane's rows were copied by other lanes
+            if (wr != nullptr) {                     // inherited rows: materialise them in the own buffer
+                const double *slot = ring + (size_t)(b % DEPTH) * (BR * 4) + lane * 2;
+                double *dst = wr + (size_t)b * (BR * 4);
+                const int row0 = b * BR + (lane >> 1);
+#pragma unroll
+                for (int i = 0; i < 2 * RPL; ++i)
+                    if (row0 + 16 * i < nrows)
+                        *reinterpret_cast<double2 *>(dst + i * 64) = *reinterpret_cast<const double2 *>(slot + i * 64);
+            }
             const double *mine = ring + (size_t)(b % DEPTH) * (BR * 4) + lane * 4;
             double2 lo[RPL], hi[RPL];
 #pragma unroll

@@ -356,6 +356,12 @@ struct EquArgs {
     const int *idx;           // optional list of the states to compute (sharded mode); nullptr = all
     int n_skips;
     EquSkip skips[EQU_MAX_SKIPS];
+    // read-through (see SliceArgs): states whose flipped neuron lies in the last hidden layer read its rows
+    // from the parent's level buffer
+    const int *bucket;        // per state of the level, nullptr = nobody
+    const int *parent;
+    int lb, prev_lb, D;
+    const double *alt_in;     // rows of the last hidden layer of the previous level's state 0
 };
 
 __device__ __forceinline__ double masked_chain(const double *w, const double *rows, const uint32_t *key, int bit0,
@@ -375,7 +381,9 @@ __global__ void equ_kernel(const EquArgs a)
     if (t >= a.S * 4) return;
     const int s = a.idx ? a.idx[t >> 2] : (t >> 2), c = t & 3;
     const uint32_t *key = a.keys + (size_t)s * a.kw;
-    double v = masked_chain(a.w, a.in + (size_t)s * a.in_stride, key, a.bit0, a.K, c);
+    const double *rows = a.in + (size_t)s * a.in_stride;
+    if (a.bucket != nullptr && a.bucket[s] == a.D) rows = a.alt_in + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.in_stride;
+    double v = masked_chain(a.w, rows, key, a.bit0, a.K, c);
     if (c == 3) v += a.bias;
     for (int i = 0; i < a.n_skips; ++i) {
         const EquSkip &sk = a.skips[i];

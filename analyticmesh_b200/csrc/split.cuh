@@ -74,7 +74,19 @@ struct SliceArgs {
     long long slice_stride;     // bytes between digit planes (ncap * pitch)
     double *scale;              // [S * 4]  2^(e - 6)
     int tile_stride, tile_offset;   // this launch handles the slots of tiles tile_offset, tile_offset + tile_stride, ...
+    // read-through: slots >= alt_from_slot take the rows of this layer from their PARENT's level buffer (they
+    // are identical to the parent's and are not copied first; clip_kernel materialises them later)
+    int alt_from_slot;              // S (or more) = no such slots
+    const double *alt_src;          // rows of this layer of the previous level's state 0
+    const int *parent;              // global state id of the parent, indexed by global state id
+    int lb, prev_lb;                // first state id of this / the previous level
 };
+
+__device__ __forceinline__ const double *slice_rows_of(const SliceArgs &a, int slot, int s)
+{
+    if (slot >= a.alt_from_slot) return a.alt_src + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.stride;
+    return a.src + (size_t)s * a.stride;
+}
 
 template <int SD>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a)
@@ -83,7 +95,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a)
     const int lane = threadIdx.x & 31;
     if (slot >= a.S || (slot / SP_BS) % a.tile_stride != a.tile_offset) return;
     const int s = a.perm ? a.perm[slot] : slot;
-    const double *rows = a.src + (size_t)s * a.stride;
+    const double *rows = slice_rows_of(a, slot, s);
     const uint32_t *key = a.keys + (size_t)s * a.kw;
 
     auto active = [&](int k) -> bool {
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(128) slice_rows_reg_kernel(const SliceArgs a)
     const int lane = threadIdx.x & 31;
     if (slot >= a.S || (slot / SP_BS) % a.tile_stride != a.tile_offset) return;
     const int s = a.perm ? a.perm[slot] : slot;
-    const double *rows = a.src + (size_t)s * a.stride;
+    const double *rows = slice_rows_of(a, slot, s);
     const uint32_t *key = a.keys + (size_t)s * a.kw;
 
     double v[NIT][4][4];

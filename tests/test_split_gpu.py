@@ -73,3 +73,17 @@ def test_against_reference_golden(fname):
     assert hashlib.sha256(b"".join(sorted(ef))).hexdigest() == g["keys_sha256"]
     v, _, _ = eng["mesh"]
     assert np.abs(case["info"].forward(v)[0]).max() <= max(g["max_abs_f"], 1e-12) + 1e-12
+
+
+def test_read_through_of_parent_rows_equals_copying(monkeypatch):
+    """Children read the rows they inherit straight from the parent's level buffer (clip_kernel materialises
+    them on the way); AM_B200_READ_THROUGH=0 restores copy_parent_rows_kernel: same bytes out."""
+    case = build_case("mlp8x512s_cube")
+    a = parity.run_engine(case, combine=False)
+    monkeypatch.setenv("AM_B200_READ_THROUGH", "0")
+    b = parity.run_engine(case, combine=False)
+    assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["edges"], b["edges"])
+    assert np.array_equal(a["xyz"], b["xyz"]) and np.array_equal(a["face_off"], b["face_off"])
+    monkeypatch.setenv("AM_B200_INCREMENTAL", "0")
+    c = parity.run_engine(case, combine=False)
+    assert np.array_equal(a["keys"], c["keys"]) and np.array_equal(a["xyz"], c["xyz"])
