@@ -1394,7 +1394,7 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
             int kmax = 3;
             for (int l = 1; l <= h->D; ++l) kmax = std::max(kmax, h->n[l]);
             // default: wide layers go to the tcgen05 split-integer path, narrow ones (tiles mostly padding) to FP64 DMMA
-            h->gemm_variant = (kmax >= 256) ? 2 : 0;   // measured: 128-wide 16.2 (DMMA) vs 10.0 M faces/s, 500-wide 12.6 vs 15.5
+            h->gemm_variant = (kmax >= 256 && kmax <= 8192) ? 2 : 0;   // measured: 128-wide 16.2 (DMMA) vs 10.0 M faces/s, 500-wide 12.6 vs 15.5
             if (const char *e = getenv("AM_B200_GEMM_VARIANT")) h->gemm_variant = atoi(e);
             auto prep = [&](auto cfg, auto kern) {
                 const size_t need = decltype(cfg)::smem_bytes(kmax);
