@@ -344,6 +344,16 @@ def main():
             "clocks": clocks,
             "roofline": roofline(variant, split_digits, achieved, peak, gemm_launches, gemm_ms, gemm_flops),
         }
+        try:        # reported baseline: the reference's own CUDA build on a B200 (golden-vector run, same network)
+            g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_mlp8x512s_cube.json")))
+            out["reference_cuda_b200"] = {
+                "value": g["timing"]["faces_per_sec"], "unit": UNIT, "faces": g["n_faces"],
+                "am_time_s": min(g["timing"]["am_time"]),
+                "note": "unmodified reference (baseline/build_ref.sh, sm_100) on one B200, same 8x512 network clipped "
+                        "by a cube (80 493 faces; the reference's fixed 2^23 vertex arena cannot hold the full mesh), "
+                        "measured by tests/golden/make_golden_ref.py"}
+        except Exception:
+            pass
         if world == 1 and not args.no_cpu_baseline:
             f, s, n = cpu_reference_sample(info, points, states, args.ref_states)
             out["cpu_baseline"] = {"value": f / s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
