@@ -367,8 +367,23 @@ struct EquArgs {
 __device__ __forceinline__ double masked_chain(const double *w, const double *rows, const uint32_t *key, int bit0,
                                                int K, int c)
 {
+    // same ascending-k chain over the active rows; the loads of four rows are issued unconditionally and ahead of
+    // the chain (memory-level parallelism), only the FMAs are predicated
     double acc = 0.0;
-    for (int k = 0; k < K; ++k) {
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+        const int bit = bit0 + k;
+        const uint32_t lo = key[bit >> 5], hi = ((bit & 31) > 28) ? key[(bit >> 5) + 1] : 0u;
+        const uint32_t m = __funnelshift_r(lo, hi, bit & 31);
+        const double r0 = rows[(size_t)k * 4 + c], r1 = rows[(size_t)k * 4 + 4 + c];
+        const double r2 = rows[(size_t)k * 4 + 8 + c], r3 = rows[(size_t)k * 4 + 12 + c];
+        const double w0 = w[k], w1 = w[k + 1], w2 = w[k + 2], w3 = w[k + 3];
+        if (m & 1u) acc = fma(w0, r0, acc);
+        if (m & 2u) acc = fma(w1, r1, acc);
+        if (m & 4u) acc = fma(w2, r2, acc);
+        if (m & 8u) acc = fma(w3, r3, acc);
+    }
+    for (; k < K; ++k) {
         const int bit = bit0 + k;
         if ((key[bit >> 5] >> (bit & 31)) & 1u) acc = fma(w[k], rows[(size_t)k * 4 + c], acc);
     }
