@@ -14,7 +14,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda.h>
@@ -1694,55 +1696,79 @@ int am_export(am_handle *h, const char *path, int is_polymesh, int is_float32)
     }
     const long long nS = h->n_states;
     const long long nV = h->stats.n_vertices;
-    long long nF = 0, nT = 0;
-    for (long long s = 0; s < nS; ++s) {
-        const long long k = h->h_face_off[s + 1] - h->h_face_off[s];
-        if (k >= 3) { ++nF; nT += k - 2; }
-    }
+    // The body is assembled by a few host threads: every thread owns a contiguous range of states, counts its
+    // faces first (so that its byte offset is known) and then writes its records in place.
+    const int T = (int)std::max<long long>(1, std::min<long long>({(long long)std::thread::hardware_concurrency(), 16LL,
+                                                                    nS / 65536 + 1}));
+    std::vector<long long> cF(T + 1, 0), cT(T + 1, 0), cC(T + 1, 0);       // faces, fan triangles, corners per range
+    auto range = [&](int t) { return std::make_pair(nS * t / T, nS * (t + 1) / T); };
+    auto run_threads = [&](auto &&fn) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto &x : th) x.join();
+    };
+    run_threads([&](int t) {
+        const auto r = range(t);
+        long long f = 0, tr = 0, c = 0;
+        for (long long s = r.first; s < r.second; ++s) {
+            const long long k = h->h_face_off[s + 1] - h->h_face_off[s];
+            if (k >= 3) { ++f; tr += k - 2; c += k; }
+        }
+        cF[t + 1] = f; cT[t + 1] = tr; cC[t + 1] = c;
+    });
+    for (int t = 0; t < T; ++t) { cF[t + 1] += cF[t]; cT[t + 1] += cT[t]; cC[t + 1] += cC[t]; }
+    const long long nF = cF[T], nT = cT[T];
     // header bytes exactly as reference backend/inc/polymesh.h:368-377
     const char *ft = is_float32 ? "float" : "double";
     std::string head = "ply\nformat binary_little_endian 1.0\nelement vertex " + std::to_string(nV) + "\nproperty " + ft +
                        " x\nproperty " + ft + " y\nproperty " + ft + " z\nelement face " +
                        std::to_string(is_polymesh ? nF : nT) + "\nproperty list uchar int vertex_index\nend_header\n";
     const size_t vbytes = (size_t)nV * 3 * (is_float32 ? 4 : 8);
-    const size_t fbytes = is_polymesh ? (size_t)nF + (size_t)h->stats.n_corners * 4 : (size_t)nT * 13;
-    std::vector<unsigned char> buf(head.size() + vbytes + fbytes);
-    unsigned char *w = buf.data();
-    memcpy(w, head.data(), head.size());
-    w += head.size();
-    if (is_float32) {
-        float *o = reinterpret_cast<float *>(w);
-        for (size_t i = 0; i < (size_t)nV * 3; ++i) { const float f = (float)h->h_vertices[i]; memcpy(o + i, &f, 4); }
-    } else if (vbytes) {
-        memcpy(w, h->h_vertices.data(), vbytes);
-    }
-    w += vbytes;
-    for (long long s = 0; s < nS; ++s) {
-        const long long fo = h->h_face_off[s];
-        const int k = (int)(h->h_face_off[s + 1] - fo);
-        if (k < 3) continue;
-        const int *idx = h->h_corner_vid.data() + fo;
-        if (is_polymesh) {
-            *w++ = (unsigned char)k;
-            memcpy(w, idx, (size_t)k * 4);
-            w += (size_t)k * 4;
-        } else {
-            for (int j = 0; j + 2 < k; ++j) {   // fan (0, j+1, j+2), reference polymesh.h:405-416
-                *w++ = 3;
-                memcpy(w, idx, 4);
-                memcpy(w + 4, idx + j + 1, 4);
-                memcpy(w + 8, idx + j + 2, 4);
-                w += 12;
+    const size_t fbytes = is_polymesh ? (size_t)nF + (size_t)cC[T] * 4 : (size_t)nT * 13;
+    const size_t total = head.size() + vbytes + fbytes;
+    std::unique_ptr<unsigned char[]> buf(new unsigned char[total]);           // not zero-filled: every byte is written
+    memcpy(buf.get(), head.data(), head.size());
+    unsigned char *vout = buf.get() + head.size();
+    unsigned char *fout = vout + vbytes;
+    run_threads([&](int t) {
+        // vertices: this thread's share of the coordinate array
+        const size_t n3 = (size_t)nV * 3, v0 = n3 * t / T, v1 = n3 * (t + 1) / T;
+        if (is_float32) {
+            float *o = reinterpret_cast<float *>(vout);
+            for (size_t i = v0; i < v1; ++i) o[i] = (float)h->h_vertices[i];
+        } else if (v1 > v0) {
+            memcpy(vout + v0 * 8, h->h_vertices.data() + v0, (v1 - v0) * 8);
+        }
+        // faces of the states in this thread's range
+        const auto r = range(t);
+        unsigned char *w = fout + (is_polymesh ? (size_t)cF[t] + (size_t)cC[t] * 4 : (size_t)cT[t] * 13);
+        for (long long s = r.first; s < r.second; ++s) {
+            const long long fo = h->h_face_off[s];
+            const int k = (int)(h->h_face_off[s + 1] - fo);
+            if (k < 3) continue;
+            const int *idx = h->h_corner_vid.data() + fo;
+            if (is_polymesh) {
+                *w++ = (unsigned char)k;
+                memcpy(w, idx, (size_t)k * 4);
+                w += (size_t)k * 4;
+            } else {
+                for (int j = 0; j + 2 < k; ++j) {   // fan (0, j+1, j+2), reference polymesh.h:405-416
+                    *w++ = 3;
+                    memcpy(w, idx, 4);
+                    memcpy(w + 4, idx + j + 1, 4);
+                    memcpy(w + 8, idx + j + 2, 4);
+                    w += 12;
+                }
             }
         }
-    }
+    });
     FILE *f = fopen(path, "wb");
     if (!f) {
         h->err = std::string("am_export: cannot open ") + path;
         return AM_ERR_IO;
     }
-    const size_t total = (size_t)(w - buf.data());
-    const size_t wr = fwrite(buf.data(), 1, total, f);
+    const size_t wr = fwrite(buf.get(), 1, total, f);
     fclose(f);
     if (wr != total) {
         h->err = std::string("am_export: short write to ") + path;
