@@ -1066,11 +1066,8 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
     ca.counters = h->counters.as<unsigned long long>();
     const unsigned cgrid = (unsigned)((n + CLIP_WARPS - 1) / CLIP_WARPS);
-    switch (h->clip_minb) {   // AM_B200_CLIP_MINB: tuning knob (resident CTAs per SM / rows per lane / ring depth)
+    switch (h->clip_minb) {   // AM_B200_CLIP_MINB: 2 = two CTAs/SM, no spills (default); 3 = three CTAs/SM
         case 3: clip_kernel<3, 2, 3><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 3), st>>>(ca); break;
-        case 4: clip_kernel<2, 2, 4><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 4), st>>>(ca); break;
-        case 5: clip_kernel<2, 2, 5><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 5), st>>>(ca); break;
-        case 6: clip_kernel<2, 1, 6><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(1, 6), st>>>(ca); break;
         default: clip_kernel<2, 2, 3><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 3), st>>>(ca); break;
     }
     ++h->stats.n_launches;
@@ -1387,9 +1384,6 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         if (const char *e = getenv("AM_B200_INCREMENTAL")) h->incremental = atoi(e) != 0;
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
         CK(cudaFuncSetAttribute(clip_kernel<3, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
-        CK(cudaFuncSetAttribute(clip_kernel<2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 4)));
-        CK(cudaFuncSetAttribute(clip_kernel<2, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 5)));
-        CK(cudaFuncSetAttribute(clip_kernel<2, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(1, 6)));
         if (const char *e = getenv("AM_B200_CLIP_MINB")) h->clip_minb = atoi(e);
         h->counters.reserve(CNT_NUM * 8);
         {

@@ -16,10 +16,18 @@
 //                  reference's vertex formula (inc/kernel.h:555-573) -- never an interpolation, so
 //                  final coordinates do not depend on the clipping order.
 //
-// The polygon starts as a large square (artificial edges, ids < 0) in the level plane centred on
-// the state's seed point; a final polygon that still has an artificial edge is unbounded and is
-// dropped (counted).  The loop is kept counter-clockwise around +w_equ, which is the reference's
-// output orientation (inc/kernel.h:1349-1353); flip_insideout reverses it.
+// The polygon starts as a square (artificial edges, ids < 0) in the level plane centred on the state's
+// seed point and sized from the parent's polygon; a final polygon that still has an artificial edge is
+// retried with a larger square and finally dropped as unbounded (counted).  The loop is kept
+// counter-clockwise around +w_equ, which is the reference's output orientation (inc/kernel.h:1349-1353);
+// flip_insideout reverses it.
+//
+// Streaming: the constraints of a state are four contiguous row segments -- the shared layer-1 table, the
+// rows the state inherits from its parent (read from the PARENT's level buffer and stored into the state's
+// own buffer on the way: this replaces a separate copy kernel), the state's own rows, the extra
+// constraints.  Each segment is streamed in 64-row blocks through a per-warp cp.async ring; a copy
+// instruction moves 32 consecutive 16-byte pieces (512 B, fully coalesced), every lane then tests two rows
+// against the polygon's vertices (each vertex load serves both rows).
 //
 // Output convention (shared with the oracle wrapper): vertices v_0..v_{k-1}; edge id g_i is the
 // constraint that carries the segment v_i -> v_{i+1}; the cycle is rotated so that g_0 is minimal.
@@ -162,8 +170,7 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
     }
     __syncwarp();
 
-    // Every lane streams its own two rows of each 64-row block through a private shared-memory ring with
-    // cp.async, so the rows of the next CLIP_DEPTH-1 blocks are in flight without holding registers.
+    // per-warp ring of DEPTH blocks of RPL * 32 rows: the next DEPTH-1 blocks are in flight without holding registers
     double *ring = s_ring + (size_t)wib * DEPTH * (RPL * 32) * 4;
     // applies the cutting planes of one 32-row half block, one at a time in row order (p, rs: this lane's row)
     auto apply_cuts = [&](unsigned long long todo, const double (&p)[RPL][4], const double (&rs)[RPL], int ebase) {

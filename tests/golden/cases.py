@@ -43,6 +43,7 @@ CASES = {
     "sphere": (zoo.sphere, 256, None),
     "mlp4x128s": (lambda: zoo.sal(depth=4, width=128), 256, None),
     "mlp8x512s_cube": (lambda: zoo.sal(depth=8, width=512), 256, "auto"),
+    "mlp3x256s_cube": (lambda: zoo.sal(depth=3, width=256), 64, "auto"),    # small, wide enough for the tcgen05 path
 }
 
 

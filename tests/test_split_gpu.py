@@ -37,7 +37,7 @@ def _planes(case, n, sd, monkeypatch):
 
 
 @pytest.mark.parametrize("name,sd", [("mlp4x128s", 7), ("skipnet", 7), ("chair_cube", 7), ("sphere", 7),
-                                     ("mlp4x128s", 6), ("mlp4x128s", 8), ("mlp8x512s_cube", 7)])
+                                     ("mlp4x128s", 6), ("mlp4x128s", 8), ("mlp8x512s_cube", 7), ("mlp3x256s_cube", 7)])
 def test_planes_equal_integer_restatement(name, sd, monkeypatch, oracle_lib):
     case = build_case(name)
     n = 37 if case["info"].state_len < 2000 else 19
@@ -51,7 +51,7 @@ def test_planes_equal_integer_restatement(name, sd, monkeypatch, oracle_lib):
     assert np.allclose(equ[0], e, rtol=0, atol=1e-11 * max(1.0, np.abs(e).max()))
 
 
-@pytest.mark.parametrize("name", ["skipnet", "chair", "mlp4x128s"])
+@pytest.mark.parametrize("name", ["skipnet", "chair", "mlp4x128s", "mlp3x256s_cube"])
 def test_region_set_and_loops_match_oracle(oracle_lib, name):
     case = build_case(name)
     eng = parity.run_engine(case)
