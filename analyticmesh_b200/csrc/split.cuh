@@ -18,13 +18,16 @@
 // i.e. the rounding of the result is at the level of an FP64 dot product; the dropped products
 // (i + j >= SD) are below 2^-50 of max|w| max|p| K.
 //
-// Kernel layout (one CTA per 128 output neurons x 16 states tile, 192 threads):
+// Kernel layout (persistent: one 192-thread CTA per SM strides over tiles of 128 output neurons x 16 states):
 //   warp 0    TMA producer: per 32-byte K step one 3-D box of the weight digits [SD][128][32] and one of
-//             the plane digits [SD][64][32] (SWIZZLE_32B), multi-stage mbarrier ring
-//   warp 1    TMEM allocation (512 columns) + single-thread MMA issue: for weight digit i ONE
+//             the plane digits [SD][64][32] (SWIZZLE_32B), multi-stage mbarrier ring; runs ahead into the
+//             next tile while the epilogue drains TMEM
+//   warp 1    TMEM allocation (512 columns, once) + single-thread MMA issue: for weight digit i ONE
 //             instruction covers the plane digits j = 0 .. SD-1-i, because their accumulators
 //             g = i + j are adjacent 64-column windows of TMEM (N = 64 (SD - i), cut at 256)
-//   warps 2-5 epilogue: tcgen05.ld of the SD accumulators, FP64 Horner, scale, bias, 16-byte stores
+//   warps 2-5 epilogue: tile constants staged in shared memory behind the MMAs, tcgen05.ld of the SD
+//             accumulators, exact int -> double, FP64 Horner, scale, bias, input-skip addend, 16-byte stores
+// Plane digits come from slice_rows_reg_kernel (one pass, rows kept in registers) or slice_rows_kernel (any K).
 #pragma once
 #include <cuda.h>
 
