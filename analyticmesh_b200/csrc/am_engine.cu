@@ -291,9 +291,9 @@ void split_weight_digits(const double *w, int M, int K, int Mpad, int Kpad, int 
         double mx = 0.0;
         for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(w[(size_t)m * K + k]));
         int e = 0;
-        if (mx > 0.0 && mx < 1.7e308) std::frexp(mx, &e);
-        const double mul = std::ldexp(1.0, frac - e);
-        scale[m] = std::ldexp(1.0, e - 6);
+        if (mx >= 2.2250738585072014e-308 && mx < 1.7e308) std::frexp(mx, &e);      // subnormal rows count as zero
+        const double mul = std::ldexp(1.0, std::max(-1022, std::min(1023, frac - e)));
+        scale[m] = std::ldexp(1.0, std::max(-1022, e - 6));
         for (int k = 0; k < K; ++k) {
             const unsigned long long Y = split_pack(std::llrint(w[(size_t)m * K + k] * mul), sd);
             for (int t = 0; t < sd; ++t)
@@ -607,10 +607,11 @@ struct am_handle {
         const bool t = timing_on() && n_chain == 1;      // per-kernel events (the roofline of the dominant kernel)
         size_t e0 = 0;
         if (t) e0 = span_begin();
+        const unsigned sgrid = (unsigned)std::min((Sc + 3) / 4, num_sms * 3);     // persistent warps, 3 CTAs per SM
         if (w.Kpad <= 256)
-            slice_rows_reg_kernel<SD, 2><<<(unsigned)((Sc + 3) / 4), 128, 0, cs>>>(sa);
+            slice_rows_reg_kernel<SD, 2><<<sgrid, 128, 0, cs>>>(sa);
         else if (w.Kpad <= 512)
-            slice_rows_reg_kernel<SD, 4><<<(unsigned)((Sc + 3) / 4), 128, 0, cs>>>(sa);
+            slice_rows_reg_kernel<SD, 4><<<sgrid, 128, 0, cs>>>(sa);
         else
             slice_rows_kernel<SD><<<(unsigned)((Sc + 7) / 8), 256, 0, cs>>>(sa);
         ++stats.n_launches;

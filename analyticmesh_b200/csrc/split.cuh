@@ -64,6 +64,16 @@ __host__ __device__ inline unsigned long long split_pack(long long X, int SD)
     return ((unsigned long long)X + C) ^ C;
 }
 
+// exponent e with 2^(e-1) <= mx < 2^e for a normal, finite mx > 0; 0 otherwise (zero / subnormal / non-finite
+// columns produce zero digits) -- frexp() without its slow paths
+__device__ __forceinline__ int split_exponent(double mx)
+{
+    const int be = (__double2hiint(mx) >> 20) & 0x7FF;
+    return (be == 0 || be == 0x7FF) ? 0 : be - 1022;
+}
+// 2^k for -1022 <= k <= 1023
+__device__ __forceinline__ double split_pow2(int k) { return __hiloint2double((1023 + k) << 20, 0); }
+
 // ---- plane digits (B operand), one warp per state slot ------------------------------------------------
 struct SliceArgs {
     const double *src;          // rows of the input layer for state 0: [K][4]
@@ -124,10 +134,9 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a)
     for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx[c] = fmax(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
-        int e = 0;
-        if (mx[c] > 0.0 && mx[c] < 1.7e308) frexp(mx[c], &e);          // mx = f 2^e, f in [0.5, 1)
-        mul[c] = ldexp(1.0, SplitCfg<SD>::FRAC_BITS - e);
-        if (lane == 0) a.scale[(size_t)slot * 4 + c] = ldexp(1.0, e - 6);
+        const int e = split_exponent(mx[c]);                            // mx = f 2^e, f in [0.5, 1)
+        mul[c] = split_pow2(max(-1022, min(1023, SplitCfg<SD>::FRAC_BITS - e)));
+        if (lane == 0) a.scale[(size_t)slot * 4 + c] = split_pow2(max(-1022, e - 6));
     }
     // pass 2: digits; lane owns 4 consecutive k -> one 32-bit store per (digit, component)
     signed char *col0 = a.dig + (size_t)slot * 4 * a.pitch;
@@ -160,71 +169,110 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a)
 }
 
 // Same result, one pass: for K <= 128 NIT the lane keeps its rows in registers between the column
-// maximum and the digit extraction (every load is issued up front, nothing is read twice).
-template <int SD, int NIT>
-__global__ void __launch_bounds__(128) slice_rows_reg_kernel(const SliceArgs a)
-{
-    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (slot >= a.S || (slot / SP_BS) % a.tile_stride != a.tile_offset) return;
-    const int s = a.perm ? a.perm[slot] : slot;
-    const double *rows = slice_rows_of(a, slot, s);
-    const uint32_t *key = a.keys + (size_t)s * a.kw;
+// maximum and the digit extraction (every load is issued up front, nothing is read twice).  Warps are
+// persistent and software-pipelined over the slots: the dependent chain slot -> state -> (parent) -> key words
+// of the NEXT slot is fetched while the rows of the current one are in flight, so a state costs one memory
+// latency instead of four.
+template <int NIT>
+struct SliceMeta {
+    const double *rows;
+    uint32_t bits[NIT];         // activation bits of this lane's 4 rows per 128-row iteration (low 4 bits)
+};
 
-    double v[NIT][4][4];
+template <int NIT>
+__device__ __forceinline__ SliceMeta<NIT> slice_meta(const SliceArgs &a, int slot, int lane)
+{
+    SliceMeta<NIT> m;
+    const int s = a.perm ? a.perm[slot] : slot;
+    m.rows = slice_rows_of(a, slot, s);
+    const uint32_t *key = a.keys + (size_t)s * a.kw;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
         const int k0 = it * 128 + lane * 4;
-        uint32_t bits = 0;
+        m.bits[it] = 0;
         if (k0 < a.K) {
             const int bit = a.bit0 + k0, w = bit >> 5;
             const uint32_t w0 = key[w], w1 = (w + 1 < a.kw) ? key[w + 1] : 0u;
-            bits = __funnelshift_r(w0, w1, bit & 31);
+            m.bits[it] = __funnelshift_r(w0, w1, bit & 31);
         }
+    }
+    return m;
+}
+
+template <int SD, int NIT>
+__global__ void __launch_bounds__(128, 3) slice_rows_reg_kernel(const SliceArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // slots of other chains' tiles are skipped (single-chain launches take every slot)
+    auto mine = [&](int sl) { return (sl / SP_BS) % a.tile_stride == a.tile_offset; };
+    while (slot < a.S && !mine(slot)) slot += n_warps;
+    if (slot >= a.S) return;
+    SliceMeta<NIT> cur = slice_meta<NIT>(a, slot, lane);
+    while (slot < a.S) {
+        double v[NIT][4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
-            if (k0 + j < a.K && ((bits >> j) & 1u)) {
-                p = *reinterpret_cast<const double2 *>(rows + (size_t)(k0 + j) * 4);
-                q = *reinterpret_cast<const double2 *>(rows + (size_t)(k0 + j) * 4 + 2);
+        for (int it = 0; it < NIT; ++it) {
+            const int k0 = it * 128 + lane * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
+                if (k0 + j < a.K && ((cur.bits[it] >> j) & 1u)) {
+                    p = *reinterpret_cast<const double2 *>(cur.rows + (size_t)(k0 + j) * 4);
+                    q = *reinterpret_cast<const double2 *>(cur.rows + (size_t)(k0 + j) * 4 + 2);
+                }
+                v[it][j][0] = p.x; v[it][j][1] = p.y; v[it][j][2] = q.x; v[it][j][3] = q.y;
             }
-            v[it][j][0] = p.x; v[it][j][1] = p.y; v[it][j][2] = q.x; v[it][j][3] = q.y;
         }
-    }
-    double mul[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        double mx = 0.0;
-#pragma unroll
-        for (int it = 0; it < NIT; ++it)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mx = fmax(mx, fabs(v[it][j][c]));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        int e = 0;
-        if (mx > 0.0 && mx < 1.7e308) frexp(mx, &e);
-        mul[c] = ldexp(1.0, SplitCfg<SD>::FRAC_BITS - e);
-        if (lane == 0) a.scale[(size_t)slot * 4 + c] = ldexp(1.0, e - 6);
-    }
-    signed char *col0 = a.dig + (size_t)slot * 4 * a.pitch;
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        const int k0 = it * 128 + lane * 4;
-        if (k0 >= a.Kpad) continue;
+        int next = slot + n_warps;
+        while (next < a.S && !mine(next)) next += n_warps;
+        SliceMeta<NIT> nxt = cur;
+        if (next < a.S) nxt = slice_meta<NIT>(a, next, lane);        // in flight together with the rows above
+
+        double mul[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            unsigned long long Y[4];
+            double mx = 0.0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) Y[j] = split_pack(__double2ll_rn(v[it][j][c] * mul[c]), SD);
+            for (int it = 0; it < NIT; ++it)
 #pragma unroll
-            for (int t = 0; t < SD; ++t) {
-                const int p = SD - 1 - t;
-                uint32_t w = 0;
+                for (int j = 0; j < 4; ++j) mx = fmax(mx, fabs(v[it][j][c]));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) w |= (uint32_t)((Y[j] >> (8 * p)) & 0xFFull) << (8 * j);
-                *reinterpret_cast<uint32_t *>(col0 + (size_t)t * a.slice_stride + (size_t)c * a.pitch + k0) = w;
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const int e = split_exponent(mx);
+            mul[c] = split_pow2(max(-1022, min(1023, SplitCfg<SD>::FRAC_BITS - e)));
+            if (lane == 0) a.scale[(size_t)slot * 4 + c] = split_pow2(max(-1022, e - 6));
+        }
+        signed char *col0 = a.dig + (size_t)slot * 4 * a.pitch;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int k0 = it * 128 + lane * 4;
+            if (k0 >= a.Kpad) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t lo[4], hi[4];
+                signed char *dst = col0 + (size_t)c * a.pitch + k0;          // digit plane 0; planes are slice_stride apart
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned long long Y = split_pack(__double2ll_rn(v[it][j][c] * mul[c]), SD);
+                    lo[j] = (uint32_t)Y;
+                    hi[j] = (uint32_t)(Y >> 32);
+                }
+#pragma unroll
+                for (int t = 0; t < SD; ++t) {
+                    // digit t = byte p of the four packed values -> one word, three byte permutes
+                    const int p = SD - 1 - t, b = p & 3;
+                    const uint32_t sel = (uint32_t)(b | ((4 + b) << 4));
+                    const uint32_t t01 = __byte_perm(p < 4 ? lo[0] : hi[0], p < 4 ? lo[1] : hi[1], sel);
+                    const uint32_t t23 = __byte_perm(p < 4 ? lo[2] : hi[2], p < 4 ? lo[3] : hi[3], sel);
+                    *reinterpret_cast<uint32_t *>(dst) = __byte_perm(t01, t23, 0x5410);
+                    dst += a.slice_stride;
+                }
             }
         }
+        cur = nxt;
+        slot = next;
     }
 }
 

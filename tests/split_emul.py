@@ -13,7 +13,7 @@ import numpy as np
 def _exponent(mx):
     """e with mx = f * 2^e, f in [0.5, 1); 0 where mx == 0."""
     _, e = np.frexp(mx)
-    return np.where(mx > 0, e, 0).astype(np.int64)
+    return np.where((mx >= np.finfo(np.float64).tiny) & np.isfinite(mx), e, 0).astype(np.int64)
 
 
 def digits(x, e, sd):
