@@ -187,4 +187,94 @@ __global__ void index_corners_kernel(const long long *owner, const uint32_t *vid
     }
 }
 
+// ---- digests + topology self-check (bench.py prints them, so that two runs -- 1 GPU / N GPUs, two engine
+// builds -- can be compared without moving the 11 GB of keys and polygons to the host) ---------------------
+// Positional checksum of an array of 64-bit words:  sum_i splitmix64(word_i + splitmix64(i + salt))  mod 2^64.
+// Any changed word and any two exchanged positions change the sum (up to a 2^-64 coincidence).
+__device__ __forceinline__ void digest_accumulate(unsigned long long *acc, uint64_t v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(acc, (unsigned long long)v);
+}
+
+__global__ void digest_words_kernel(const void *data, long long n_words, int word_bytes, uint64_t salt,
+                                    unsigned long long *acc)
+{
+    uint64_t sum = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        const uint64_t w = (word_bytes == 8) ? static_cast<const uint64_t *>(data)[i]
+                                             : (uint64_t) static_cast<const uint32_t *>(data)[i];
+        sum += splitmix64(w + splitmix64((uint64_t)i + salt));
+    }
+    digest_accumulate(acc, sum);
+}
+
+// Order-independent digest of the region set (one warp per state): the per-state value depends only on the
+// state's key (and its edge loop / vertex bits), the states' values are mixed once more and summed, so the
+// result does not depend on the order in which the states were visited.
+//   acc[0]: keys + edge loops ("topology": must equal the CPU oracle's value)   acc[1]: + vertex bits
+__global__ void digest_states_kernel(const uint32_t *keys, int kw, int n_words, const long long *face_off,
+                                     const int *face_edges, const double *face_xyz, long long n_states,
+                                     unsigned long long *acc)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    uint64_t topo = 0, full = 0;
+    for (long long s = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); s < n_states; s += warps) {
+        uint64_t h = 0, g = 0;
+        for (int w = lane; w < n_words; w += 32) h += word_mix((uint32_t)w, keys[(size_t)s * kw + w]);
+        const long long fo = face_off[s];
+        const int k = int(face_off[s + 1] - fo);
+        if (lane < k) {
+            h += splitmix64((uint64_t)(uint32_t)face_edges[fo + lane] + splitmix64(0xE0000000ull + (uint64_t)lane));
+            for (int c = 0; c < 3; ++c)
+                g += splitmix64((uint64_t)__double_as_longlong(face_xyz[(size_t)(fo + lane) * 3 + c]) +
+                                splitmix64(0xF0000000ull + (uint64_t)(3 * lane + c)));
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+            g += __shfl_xor_sync(0xFFFFFFFFu, g, o);
+        }
+        h += splitmix64((uint64_t)k);
+        if (lane == 0) {
+            topo += splitmix64(h);
+            full += splitmix64(h + splitmix64(g));
+        }
+    }
+    if (lane == 0 && (topo | full)) {
+        atomicAdd(acc + 0, (unsigned long long)topo);
+        atomicAdd(acc + 1, (unsigned long long)full);
+    }
+}
+
+// Edge incidence: the polygon edge of state s carried by neuron e is shared with the state whose key differs
+// in bit e.  out[0] boundary edges (extra constraints), out[1] neuron edges whose sibling state was visited
+// and has the same edge (each shared edge is counted from both sides), out[2] sibling state never visited,
+// out[3] sibling visited but without that edge.
+template <int G>
+__global__ void edge_incidence_kernel(const StitchArgs a, unsigned long long *out)
+{
+    cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
+    const int sid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (sid >= a.n_states) return;
+    const long long fo = a.face_off[sid];
+    const int k = int(a.face_off[sid + 1] - fo);
+    unsigned n[4] = {0, 0, 0, 0};
+    for (int i = 0; i < k; ++i) {
+        const int e = a.face_edges[fo + i];
+        if (e < 0 || e >= a.L) { ++n[0]; continue; }
+        const int t = lookup_sibling<G>(tile, a.keys, a.hsum, a.kw, a.kw4, a.table, sid, e, -1);
+        if (t < 0) { ++n[2]; continue; }
+        const long long fo2 = a.face_off[t];
+        const int k2 = int(a.face_off[t + 1] - fo2);
+        bool has = false;
+        for (int j = 0; j < k2; ++j) has |= (a.face_edges[fo2 + j] == e);
+        ++n[has ? 1 : 3];
+    }
+    if (tile.thread_rank() == 0)
+        for (int c = 0; c < 4; ++c)
+            if (n[c]) atomicAdd(out + c, (unsigned long long)n[c]);
+}
+
 }  // namespace amb

@@ -32,13 +32,13 @@ class AmStats(ctypes.Structure):
         "n_overflow", "n_over_vertmax", "n_inconsistent", "n_vertices", "n_stitch_miss", "max_level_states",
         "n_launches")] + \
         [(n, ctypes.c_double) for n in ("seconds_march", "seconds_compose", "seconds_clip", "seconds_frontier",
-                                        "compose_flops")]
+                                        "compose_flops")] + [("n_tensors_reloaded", ctypes.c_int64)]
 
 
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",
            "am_key_words", "am_state_len", "am_copy_states", "am_copy_faces", "am_copy_mesh", "am_load_weights",
            "am_debug_planes", "am_compose_profile", "am_kernel_profile", "am_gemm_variant", "am_fp64_peak_tflops", "am_set_shard", "am_nccl_unique_id",
-           "am_set_shard_nccl", "am_ply_parse_faces",
+           "am_set_shard_nccl", "am_gather_states", "am_digest", "am_edge_incidence", "am_ply_parse_faces",
            "am_ply_pack_faces")
 
 
@@ -279,6 +279,44 @@ def mesh():
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     _err(lib().am_copy_mesh(_handle, p(v), p(fs), p(fi)), "mesh")
     return v, fs, fi
+
+
+def gather_states(ids):
+    """The listed states only: dict(keys (n, kw), counts (n,), edges (n, 32), xyz (n, 32, 3), parent, via, seedpt (n, 4))."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    n, kw = len(ids), lib().am_key_words(_handle)
+    out = dict(keys=np.zeros((n, kw), np.uint32), counts=np.zeros(n, np.int32), edges=np.zeros((n, 32), np.int32),
+               xyz=np.zeros((n, 32, 3), np.float64), parent=np.zeros(n, np.int32), via=np.zeros(n, np.int32),
+               seedpt=np.zeros((n, 4), np.float64))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    fn = lib().am_gather_states
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 7
+    _err(fn(_handle, p(ids), n, p(out["keys"]), p(out["counts"]), p(out["edges"]), p(out["xyz"]), p(out["parent"]),
+            p(out["via"]), p(out["seedpt"])), "gather_states")
+    return out
+
+
+def digest():
+    """Device-side checksums of the last march (include/am_b200.h: am_digest) as a dict; `ordered` / `region_set`
+    are hex strings that two runs can compare (1 GPU vs N GPUs, two builds)."""
+    import hashlib
+    buf = (ctypes.c_uint64 * 8)()
+    fn = lib().am_digest
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    _err(fn(_handle, buf), "digest")
+    v = [int(x) for x in buf]
+    hx = lambda xs: hashlib.sha256(b"".join(int(x).to_bytes(8, "little") for x in xs)).hexdigest()[:32]  # noqa: E731
+    return dict(ordered=hx(v[0:4] + v[6:8]), region_set=hx([v[4], v[6], v[7]]), region_set_with_vertices=hx([v[5], v[6], v[7]]),
+                topology_sum=v[4], n_states=v[6], n_corners=v[7], raw=v)
+
+
+def edge_incidence():
+    """dict(boundary, matched, neighbour_missing, neighbour_without_edge) -- include/am_b200.h: am_edge_incidence."""
+    buf = (ctypes.c_int64 * 4)()
+    fn = lib().am_edge_incidence
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    _err(fn(_handle, buf), "edge_incidence")
+    return dict(boundary=int(buf[0]), matched=int(buf[1]), neighbour_missing=int(buf[2]), neighbour_without_edge=int(buf[3]))
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)

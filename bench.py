@@ -71,6 +71,7 @@ def roofline(variant, split_digits, achieved, fp64_peak, launches, ms, flops):
         traffic = ncu_traffic("compose_gemm_kernel", flops / max(launches, 1))
         return {"bound": "fp64", "kernel": "compose_gemm_kernel", "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                "traffic_source": "scaled from the committed ncu --set full capture (profiles/ncu_traffic.json), not measured in this run",
                 "launches": launches, "avg_launch_ms": avg_ms,
                 "peak_source": "DFMA loop measured in this process (am_fp64_peak_tflops); FP64 is not in "
                                "MEASURED_PEAKS.json; tools/fp64_peak.cu: DFMA 37.0, DMMA 37.0, cuBLAS DGEMM 35.8"}
@@ -84,6 +85,7 @@ def roofline(variant, split_digits, achieved, fp64_peak, launches, ms, flops):
     peak = 2.0 * bf16 / products
     return {"bound": "tensor", "kernel": "split_gemm_kernel", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic("split_gemm_kernel", flops / max(launches, 1)),
+            "traffic_source": "scaled from the committed ncu --set full capture (profiles/ncu_traffic.json), not measured in this run",
             "launches": launches, "avg_launch_ms": avg_ms,
             "int8_tops_achieved": achieved * products, "int8_tops_peak": 2.0 * bf16, "digit_products": products,
             "peak_source": f"FP64-equivalent TFLOP/s: algorithmic 2*M*K*4*S flops of the launch; peak = int8 tensor peak / "
@@ -152,18 +154,19 @@ def run_reference_arm(args):
         return
     info, points, states, _ = build_workload(args.workload, 0, args.seeds)
     cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     for _ in range(args.warmup):
-        cpu_reference_sample(info, points, states, args.ref_states)
+        cpu_reference_sample(info, points, states, args.ref_states, threads=cores)
     faces, secs = 0, 0.0
     for _ in range(args.steps):
-        f, s, _n = cpu_reference_sample(info, points, states, args.ref_states)
+        f, s, _n = cpu_reference_sample(info, points, states, args.ref_states, threads=cores)
         faces += f
         secs += s
     v = faces / secs
     sample = f"first {args.ref_states} states of the march (LIFO batches of 1024), same network and seeds"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "note": "CPU restatement of the reference algorithm "
                    "(oracle/am_oracle.c, OpenMP); the reference itself has no CPU path"},
@@ -275,33 +278,52 @@ def main():
     e0.record()
     e_faces = 0
     d2h = 0
-    e2e_parts = {"march_host_buffers": 0.0, "combine_and_read_back": 0.0}
+    e2e_parts = {"march_host_buffers": 0.0, "combine_and_read_back": 0.0, "export_ply": 0.0}
+    ply = f"/tmp/am_b200_bench_rank{rank}.ply"
+    ply_bytes = 0
     for _ in range(args.steps):
         t0 = time.time()
         st = march(host)
         t1 = time.time()
-        if rank == 0:   # the mesh is replicated: one rank stitches it and reads it back
+        t2 = t1
+        if rank == 0:   # the mesh is replicated: one rank stitches it, reads it back and writes the PLY
             cuam.CombineMesh(scale=1.0, center=[0.0, 0.0, 0.0])
             st = cuam.stats()
             d2h = st["n_vertices"] * 24 + st["n_corners"] * 4 + (st["n_states"] + 1) * 8
+            t2 = time.time()
+            cuam.ExportMesh(file_path=ply, is_polymesh=True, is_float32=True)     # the reference's export_time phase
         e2e_parts["march_host_buffers"] += (t1 - t0) / args.steps
-        e2e_parts["combine_and_read_back"] += (time.time() - t1) / args.steps
+        e2e_parts["combine_and_read_back"] += (t2 - t1) / args.steps
+        e2e_parts["export_ply"] += (time.time() - t2) / args.steps
         e_faces += st["n_faces"]
     e1.record()
     barrier()
     e_dt = e0.elapsed_time(e1) * 1e-3
     h2d = sum(a.nbytes for a in info.weights + info.biases + info.arc_tm) + states.nbytes + points.nbytes
     clocks = sampler.stop() if rank == 0 else None
-
-    # export once (not timed in `value`): the reference's export_time phase
-    t0 = time.time()
-    export_time, ply_bytes = 0.0, 0
+    export_time = e2e_parts["export_ply"]
     if rank == 0:
-        ply = f"/tmp/am_b200_bench_rank{rank}.ply"
-        cuam.ExportMesh(file_path=ply, is_polymesh=True, is_float32=True)
-        export_time = time.time() - t0
         ply_bytes = os.path.getsize(ply)
         os.remove(ply)
+
+    # what was computed, as checksums every run prints (1 GPU vs N GPUs, this build vs the last): see cuam.digest
+    digest = cuam.digest()
+    digest.pop("raw")
+    mesh_check = None
+    if rank == 0:
+        inc = cuam.edge_incidence()
+        stc = cuam.stats()
+        n_edges = inc["matched"] // 2 + inc["boundary"] + inc["neighbour_missing"] + inc["neighbour_without_edge"]
+        mesh_check = {"edge_incidence": inc, "n_vertices": stc["n_vertices"], "n_faces": stc["n_faces"],
+                      "n_edges": n_edges, "euler_characteristic": stc["n_vertices"] - n_edges + stc["n_faces"],
+                      "n_stitch_miss": stc["n_stitch_miss"], "n_overflow": stc["n_overflow"],
+                      "n_unbounded": stc["n_unbounded"], "n_inconsistent": stc["n_inconsistent"]}
+    if world > 1:       # every rank holds the same mesh: compare the ordered digests
+        mine = torch.tensor([int(digest["ordered"][:15], 16)], dtype=torch.int64, device=dev)
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        digest["identical_on_all_ranks"] = bool(int(lo) == int(hi))
 
     if world > 1:
         t = torch.tensor([dt, e_dt], dtype=torch.float64, device=dev)
@@ -320,7 +342,7 @@ def main():
         out = {
             "metric": METRIC, "value": faces / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak",
+            "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "faces_per_step_rank0": last["n_faces"],
                        "states_per_step_rank0": last["n_states"], "bfs_levels": last["n_levels"],
@@ -330,8 +352,10 @@ def main():
                                       "all-reduce of the level's polygons per BFS level, frontier replicated"
                        if world > 1 else "single GPU",
                        "mesh_time_s": {"init_point_time": init_point_time, "init_cuda_time": init_cuda_time,
-                                       "am_time": dt / args.steps, "am_plus_combine_host_buffers": e_dt / args.steps,
-                                       "export_time": export_time, "ply_bytes": ply_bytes},
+                                       "am_time": dt / args.steps,
+                                       "am_combine_export_host_buffers": e_dt / args.steps,
+                                       "export_time": export_time, "ply_bytes": ply_bytes,
+                                       "end_to_end": init_point_time + init_cuda_time + e_dt / args.steps},
                        "engine_stream_seconds_per_step": engine_s / args.steps,
                        "e2e_wall_seconds_per_step_rank0": e2e_parts,
                        "phase_seconds_last_step_rank0": phases,
@@ -341,6 +365,8 @@ def main():
                                       if variant == 2 else "FP64 tensor-core DMMA")},
             "e2e": {"value": e_faces / e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
+            "digest": digest,
+            "mesh_check": mesh_check,
             "clocks": clocks,
             "roofline": roofline(variant, split_digits, achieved, peak, gemm_launches, gemm_ms, gemm_flops),
         }
@@ -355,7 +381,7 @@ def main():
         except Exception:
             pass
         if world == 1 and not args.no_cpu_baseline:
-            f, s, n = cpu_reference_sample(info, points, states, args.ref_states)
+            f, s, n = cpu_reference_sample(info, points, states, args.ref_states, threads=os.cpu_count() or 1)
             out["cpu_baseline"] = {"value": f / s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"first {n} states of the same march (same network, same seeds), "
                                              f"{s:.1f} s of OpenMP CPU work"}

@@ -58,6 +58,8 @@ typedef struct am_stats {
     double  seconds_clip;       /* ... in the clipping kernel */
     double  seconds_frontier;   /* ... in neighbour enumeration + visited-set kernels */
     double  compose_flops;      /* algorithmic flops executed by the composition kernels */
+    int64_t n_tensors_reloaded; /* weight matrices / transforms whose bytes changed since the previous call and were
+                                   re-staged on the device (0 when the same network is marched again) */
 } am_stats;
 
 /* replaces cuam.Init (reference backend/src/cuam.cpp:58-95, src/cuam_kernel.cu:128-148).
@@ -125,6 +127,28 @@ int am_copy_faces(const am_handle *h, int32_t *edge_ids, double *xyz);
 /* after am_combine: vertices [n_vertices][3] (scaled, double), face_sizes [n_faces],
  * face_index [n_corners of exported faces]. Host pointers only. */
 int am_copy_mesh(const am_handle *h, double *vertices, int32_t *face_sizes, int32_t *face_index);
+
+/* the listed states only (ids: state ids, host pointer): keys [n][am_key_words()], counts [n] polygon sizes,
+ * edges [n][32], xyz [n][32][3] (first counts[i] entries valid), parent / via_edge [n], seedpt [n][4] = the point
+ * on the shared edge handed to the state (x, y, z, size hint).  Any output may be NULL.  Lets a test recompute
+ * a sample of a march too large to copy (17.7 M states = 9 GB of keys) with the CPU oracle.
+ * Reference counterpart: the popped batch of backend/src/cuam_kernel.cu:53-98. */
+int am_gather_states(const am_handle *h, const int64_t *ids, int64_t n, uint32_t *keys, int32_t *counts,
+                     int32_t *edges, double *xyz, int32_t *parent, int32_t *via_edge, double *seedpt);
+
+/* Checksums of the last march, computed on the device (nothing is copied to the host):
+ *   out[0..3]  positional checksums of keys / face_off / edge ids / vertex bits in state-id order -- equal
+ *              between two runs iff numbering, topology and every coordinate bit are equal
+ *   out[4]     order-independent checksum over the states of (key, edge loop): the region set + adjacency
+ *   out[5]     the same including the vertex bits
+ *   out[6], out[7]  n_states, n_corners */
+int am_digest(am_handle *h, uint64_t out[8]);
+
+/* Edge incidence of the polygon soup (exact visited-set lookups of the state across every edge):
+ * out[0] edges on extra constraints (boundary), out[1] neuron edges matched by the neighbouring state's
+ * polygon (counted from both sides: out[1]/2 shared edges), out[2] neighbour never visited, out[3] neighbour
+ * visited but without that edge.  Closed 2-manifold <=> out[0] = out[2] = out[3] = 0. */
+int am_edge_incidence(am_handle *h, int64_t out[4]);
 
 /* debug/parity: run only the affine-composition kernels for n given states and return the
  * UNSIGNED rows planes[n][L][4] and the level planes equ[n][4] (host pointers, real type).

@@ -28,6 +28,7 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         for p in ("amo64", "amo32"):
             getattr(_lib, p + "_march").restype = ctypes.c_void_p
+            getattr(_lib, p + "_process_states").restype = ctypes.c_void_p
             getattr(_lib, p + "_n_states").restype = ctypes.c_int64
             getattr(_lib, p + "_n_faces").restype = ctypes.c_int64
             getattr(_lib, p + "_seconds").restype = ctypes.c_double
@@ -100,6 +101,72 @@ def march(info, states_bool, points, w_extra=None, b_extra=None, iso=0.0, flip=F
                                           for k in ("keys", "tab", "verts", "start", "equ")])
     getattr(L_, pfx + "_free_result")(res)
     return out
+
+
+def _collect(L_, pfx, res, dt, L):
+    res = ctypes.c_void_p(res)
+    n = getattr(L_, pfx + "_n_states")(res)
+    kw = getattr(L_, pfx + "_key_words")(res)
+    out = dict(n_states=n, n_faces=getattr(L_, pfx + "_n_faces")(res), seconds=getattr(L_, pfx + "_seconds")(res),
+               keys=np.zeros((n, kw), dtype=np.uint32), tab=np.zeros((n, TAB_LEN), dtype=np.int32),
+               verts=np.zeros((n, VERT_LEN), dtype=dt), start=np.zeros(n, dtype=np.int32),
+               equ=np.zeros((n, 4), dtype=dt), state_len=L)
+    getattr(L_, pfx + "_copy_out")(res, *[out[k].ctypes.data_as(ctypes.c_void_p)
+                                          for k in ("keys", "tab", "verts", "start", "equ")])
+    getattr(L_, pfx + "_free_result")(res)
+    return out
+
+
+def process_states(info, keys_u32, midpoints, starts, w_extra=None, b_extra=None, iso=0.0, flip=False, threads=0):
+    """The per-state stages of the reference for an explicit list of states: keys (n, >= ceil(L/32)) uint32,
+    midpoints (n, 3) the point on the shared edge, starts (n,) start edge or -1.  Same result dict as march()."""
+    dt = info.dtype
+    pfx = "amo64" if dt == np.float64 else "amo32"
+    L = info.state_len
+    kw = (L + 31) // 32
+    keys = np.ascontiguousarray(np.asarray(keys_u32, dtype=np.uint32)[:, :kw])
+    mid = np.ascontiguousarray(midpoints, dtype=dt).reshape(-1, 3)
+    st = np.ascontiguousarray(starts, dtype=np.int32).reshape(-1)
+    assert keys.shape[0] == mid.shape[0] == st.shape[0]
+    we = np.zeros((0, 3), dtype=dt) if w_extra is None else np.ascontiguousarray(w_extra, dtype=dt).reshape(-1, 3)
+    be = np.zeros((0,), dtype=dt) if b_extra is None else np.ascontiguousarray(b_extra, dtype=dt).reshape(-1)
+    args, keep = _net_args(info)
+    L_ = lib()
+    res = getattr(L_, pfx + "_process_states")(
+        *args, keys.ctypes.data_as(ctypes.c_void_p), mid.ctypes.data_as(ctypes.c_void_p),
+        st.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(keys.shape[0]), we.ctypes.data_as(ctypes.c_void_p),
+        be.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(we.shape[0]), ctypes.c_double(iso), ctypes.c_int(int(flip)),
+        ctypes.c_int(threads))
+    return _collect(L_, pfx, res, dt, L)
+
+
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def topology_sum(faces, state_len):
+    """Order-independent checksum of {key: edge loop} -- the value the engine computes on the device
+    (analyticmesh_b200/csrc/mesh.cuh digest_states_kernel, acc[0]); `faces` as returned by canonical_faces()
+    or tests.parity.engine_faces(): {key bytes: (edge ids, vertices) or None}."""
+    n_words = (state_len + 31) // 32
+    total = 0
+    for key, val in faces.items():
+        words = np.frombuffer(key + b"\0" * (4 * n_words - len(key)), dtype="<u4")
+        h = 0
+        for w in range(n_words):
+            h = (h + _splitmix64(((w + 1) << 32) | int(words[w]))) & _M64
+        edges = () if val is None else val[0]
+        for j, e in enumerate(edges):
+            h = (h + _splitmix64(((int(e) & 0xFFFFFFFF) + _splitmix64(0xE0000000 + j)) & _M64)) & _M64
+        h = (h + _splitmix64(len(edges))) & _M64
+        total = (total + _splitmix64(h)) & _M64
+    return total
 
 
 def canonical_faces(res):

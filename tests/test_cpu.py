@@ -160,6 +160,41 @@ def test_oracle_extra_constraints_and_seed_dedup(oracle_lib):
     assert twice["n_states"] == r["n_states"]
 
 
+def test_oracle_per_state_entry_reproduces_the_march(oracle_lib):
+    """process_states() (used to check a sample of a march that is too large for the CPU) gives, state by state,
+    what the whole march gave: start from any point of the face (its centroid) without a start edge, or from the
+    midpoint of one of its edges with that edge as the start edge."""
+    c = build_case("chair_cube")
+    info = c["info"]
+    r = oracle_lib.march(info, c["states"], c["points"], c["w_extra"], c["b_extra"])
+    cf = _canon(oracle_lib, r)
+    L = info.state_len
+    keys, mids, starts, want = [], [], [], []
+    for i, (k, v) in enumerate(cf.items()):
+        if v is None:
+            continue
+        kw = np.frombuffer(k + b"\0" * (4 * ((L + 31) // 32) - len(k)), dtype="<u4")
+        j = i % len(v[0])
+        keys += [kw, kw]
+        mids += [v[1].mean(0), 0.5 * (v[1][j] + v[1][(j + 1) % len(v[0])])]
+        starts += [-1, v[0][j]]
+        want += [v, v]
+    got = oracle_lib.process_states(info, np.stack(keys), np.stack(mids), starts, c["w_extra"], c["b_extra"])
+    gf = [None] * len(want)
+    assert got["n_states"] == len(want) > 1000
+    for o in range(len(want)):
+        one = {kk: got[kk][o:o + 1] for kk in ("keys", "tab", "verts")}
+        one.update(n_states=1, state_len=L)
+        (val,) = oracle_lib.canonical_faces(one).values()
+        assert val is not None and val[0] == want[o][0], (o, val, want[o][0])
+        assert np.abs(val[1] - want[o][1]).max() < 1e-9
+    # the order-independent checksum the engine computes on the device (cuam.digest) is order independent
+    items = list(cf.items())
+    assert oracle_lib.topology_sum(dict(items), L) == oracle_lib.topology_sum(dict(reversed(items)), L)
+    items[0] = (items[0][0], None)
+    assert oracle_lib.topology_sum(dict(items), L) != oracle_lib.topology_sum(cf, L)
+
+
 def test_oracle_float32_variant_runs(oracle_lib):
     c = build_case("chair_cube")
     info32 = NetInfo.from_model(c["model"], dtype=np.float32)
