@@ -29,6 +29,7 @@
 #include "frontier.cuh"
 #include "mesh.cuh"
 #include "split.cuh"
+#include "xchg.cuh"
 
 using namespace amb;
 
@@ -400,6 +401,15 @@ struct am_handle {
     void *nccl_comm = nullptr;                  // set by am_set_shard_nccl: collectives issued from C++
     DevBuf owner, xchg;
     long long shard_owned_states = 0;
+    // device-initiated exchange over NVLink peer memory (xchg.cuh; am_set_shard_p2p)
+    bool p2p = false;
+    void *xblock = nullptr;                     // this rank's exchange block (cudaMalloc + cudaIpcGetMemHandle)
+    XchgPeers xpeers{};
+    XchgLayout xlay{};
+    uint32_t xepoch = 0;
+    unsigned long long xtimeout_ns = 20000000000ull;
+    DevBuf xcursor, xcnt, xwhere, wmask;
+    bool table_sharded = false;                 // the visited set holds only the keys whose hash this rank owns
     int *h_npre = nullptr;                      // pinned
     int *h_next = nullptr;                      // pinned: bucket histogram of the NEXT level (count_winners_kernel)
     DevBuf next_counts;
@@ -458,7 +468,7 @@ struct am_handle {
                          &table, &planes, &equ, &f_cnt, &f_off, &f_edges, &f_verts, &cand_slot, &nwin, &wbase, &scan_a,
                          &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates, &lvl_planes[0], &lvl_planes[1],
                          &bucket, &perm, &bcounts, &owner, &xchg, &cmb_owner, &cmb_flag, &cmb_vid, &cmb_cvid, &cmb_verts,
-                         &digest_acc};
+                         &digest_acc, &xcursor, &xcnt, &xwhere, &wmask};
         for (DevBuf *b : all) b->release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear();
@@ -515,6 +525,8 @@ struct am_handle {
     }
     void ensure_table(size_t entries)
     {
+        const bool shard_table = p2p && shard_world > 1 && table_sharded;
+        if (shard_table) entries = entries / shard_world + entries / (4 * shard_world) + 4096;   // hash-owned share + slack
         uint64_t want = 1ull << 16;
         while (want < (uint64_t)entries * 2) want <<= 1;
         if (want <= tcap) return;
@@ -524,8 +536,8 @@ struct am_handle {
         CK(cudaMemsetAsync(table.p, 0xFF, (size_t)tcap * 8, stream));
         if (n_states > 0) {
             TableRef t{table.as<unsigned long long>(), tcap - 1};
-            rehash_kernel<<<(unsigned)((n_states + 255) / 256), 256, 0, stream>>>(hsum.as<unsigned long long>(),
-                                                                                 (int)n_states, t);
+            rehash_kernel<<<(unsigned)((n_states + 255) / 256), 256, 0, stream>>>(
+                hsum.as<unsigned long long>(), (int)n_states, t, shard_table ? shard_world : 1, shard_rank);
             ++stats.n_launches;
             CK(cudaGetLastError());
         }
@@ -1188,6 +1200,53 @@ void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc)
     CK(cudaGetLastError());
 }
 
+// The sharded counterpart of store_faces: this rank's polygons are pushed into every rank's inbox over NVLink,
+// one device-side barrier, then sizes -> prefix sum -> CSR from the own inbox (xchg.cuh).  No host
+// synchronisation, no collective library.
+void xchg_barrier(am_handle *h)
+{
+    ++h->xepoch;
+    xchg_barrier_kernel<<<1, 32, 0, h->stream>>>(h->xpeers, h->xepoch, h->xtimeout_ns, h->counters.as<unsigned long long>());
+    ++h->stats.n_launches;
+    CK(cudaGetLastError());
+}
+
+void store_faces_p2p(am_handle *h, long long sid0, int Sc, Scratch sc, const int *idx, int n_mine)
+{
+    cudaStream_t st = h->stream;
+    unsigned long long *cnt = h->counters.as<unsigned long long>();
+    if (n_mine > h->xlay.cap_states)
+        throw CapacityFail{"sharded march: " + std::to_string(n_mine) + " states of one rank in one BFS level exceed the "
+                           "exchange region (raise AM_B200_XCHG_MIB)"};
+    h->xcursor.reserve(64);
+    h->xcnt.reserve((size_t)Sc * 4, 0, false);
+    h->xwhere.reserve((size_t)Sc * 8, 0, false);
+    h->f_off.reserve((size_t)Sc * 4, 0, false);
+    CK(cudaMemsetAsync(h->xcursor.p, 0, 4, st));
+    XchgPackArgs pa{};
+    pa.idx = idx; pa.n = n_mine; pa.cnt = sc.cnt; pa.edges = sc.edges; pa.verts = sc.verts;
+    pa.cursor = h->xcursor.as<int>(); pa.p = h->xpeers; pa.lay = h->xlay; pa.counters = cnt;
+    xchg_pack_kernel<<<(unsigned)std::max(1, (n_mine + 7) / 8), 256, 0, st>>>(pa);
+    ++h->stats.n_launches;
+    xchg_barrier(h);
+    const unsigned char *own = h->xpeers.base[h->shard_rank];
+    dim3 ug((unsigned)std::max(1, std::min((Sc + 255) / 256, 64)), (unsigned)h->shard_world);
+    xchg_unpack_kernel<<<ug, 256, 0, st>>>(own, h->xlay, Sc, h->xcnt.as<int>(), h->xwhere.as<int2>(), cnt);
+    ++h->stats.n_launches;
+    CK(cudaGetLastError());
+    h->scan(h->xcnt.as<uint32_t>(), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
+    XchgCompactArgs co{};
+    co.own = own; co.lay = h->xlay; co.cnt_all = h->xcnt.as<int>(); co.off = h->f_off.as<uint32_t>();
+    co.where = h->xwhere.as<int2>(); co.S = Sc; co.sid0 = (int)sid0;
+    co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
+    co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
+    xchg_compact_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
+    ++h->stats.n_launches;
+    bump_counters_kernel<<<1, 32, 0, st>>>(cnt);
+    ++h->stats.n_launches;
+    CK(cudaGetLastError());
+}
+
 void process_level(am_handle *h, long long lb, long long le, double iso, int flip)
 {
     cudaStream_t st = h->stream;
@@ -1258,7 +1317,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
             have = true;
         }
         if (!have) CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 2) * 4, cudaMemcpyDeviceToHost, st));
-        if (sharded) CK(cudaMemsetAsync(sc.cnt, 0, (size_t)S * 4, st));   // counts of states owned elsewhere
+        if (sharded && !h->p2p) CK(cudaMemsetAsync(sc.cnt, 0, (size_t)S * 4, st));   // counts of states owned elsewhere
         h->lazy_prev = nullptr;
         if (h->prev_resident && h->lazy_ok) {        // no copy: slice / level-plane / clip kernels read the parent's rows
             h->lazy_prev = h->lvl_planes[h->prev_buf].as<double>();
@@ -1282,7 +1341,8 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         if (timing) h->span_end(t0, 1);
         if (timing) t0 = h->span_begin();
         run_clip(h, lb, sharded ? n_mine : (int)S, base, flip, sharded ? h->perm.as<int>() : nullptr, sc);
-        store_faces(h, lb, (int)S, sc);   // sharded: + the level's collectives (sizes, edges, vertices)
+        if (sharded && h->p2p) store_faces_p2p(h, lb, (int)S, sc, h->perm.as<int>(), n_mine);   // NVLink peer pushes
+        else store_faces(h, lb, (int)S, sc);   // sharded: + the level's collectives (sizes, edges, vertices)
         h->lazy_prev = nullptr;
         if (timing) h->span_end(t0, 2);
         h->prev_resident = true;
@@ -1334,6 +1394,12 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     a.counters = cnt;
     const int G = h->G;
     const unsigned gb = (unsigned)((S * G + 255) / 256);
+    const bool p2p = h->p2p && h->shard_world > 1;
+    a.world = p2p ? h->shard_world : 1;
+    a.rank = h->shard_rank;
+    a.wmask = nullptr;
+    if (p2p && S > h->xlay.mask_cap)
+        throw CapacityFail{"sharded march: a BFS level of " + std::to_string(S) + " states exceeds the winner-mask region"};
     h->dispatch_group([&](auto g) { expand_insert_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
     ++h->stats.n_launches;
     {
@@ -1342,7 +1408,18 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         for (int l = 1; l <= h->D + 1; ++l) lo.off[l] = h->off[l];
         a.owner = h->shard_world > 1 ? h->owner.as<uint8_t>() : nullptr;
         CK(cudaMemsetAsync(h->next_counts.p, 0, (size_t)(h->D + 3) * 4, st));
-        count_winners_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a, lo, h->next_counts.as<int>(), h->shard_rank);
+        if (p2p) {   // winners of the candidates whose hash this rank owns -> every rank; OR after the barrier
+            h->wmask.reserve((size_t)S * 4, 0, false);
+            xchg_push_masks_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a, h->xpeers, h->xlay);
+            ++h->stats.n_launches;
+            xchg_barrier(h);
+            xchg_merge_masks_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(
+                a, h->xpeers.base[h->shard_rank], h->xlay, h->shard_world, h->wmask.as<uint32_t>(), lo,
+                h->next_counts.as<int>(), h->shard_rank);
+            a.wmask = h->wmask.as<uint32_t>();
+        } else {
+            count_winners_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a, lo, h->next_counts.as<int>(), h->shard_rank);
+        }
         ++h->stats.n_launches;
         CK(cudaGetLastError());
     }
@@ -1350,6 +1427,12 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     CK(cudaMemcpyAsync(h->h_next, h->next_counts.p, (size_t)(h->D + 3) * 4, cudaMemcpyDeviceToHost, st));
     h->read_counters();                                   // the one host sync of the level
     h->next_valid = true;
+    if (h->h_counters[CNT_XCHG_ERROR] != 0) {
+        const unsigned long long e = h->h_counters[CNT_XCHG_ERROR];
+        throw CudaFail{"sharded march: the exchange over peer memory failed (" + std::to_string(e & 0xFFFF) +
+                       " barrier time-outs, " + std::to_string((e >> 16) & 0xFFFF) + " bad records, " +
+                       std::to_string(e >> 32) + " polygons beyond the inbox capacity)"};
+    }
     const long long n_new = (long long)h->h_counters[CNT_NEW];
     if (h->n_states + n_new >= (1LL << 31) - 1) throw CapacityFail{"more than 2^31 states"};
     h->ensure_states((size_t)(h->n_states + n_new));
@@ -1366,6 +1449,24 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     }
     if (timing) h->span_end(t0, 3);
     h->n_states += n_new;
+}
+
+// After a sharded march the visited set of this rank holds only the keys whose hash it owns; stitching and the
+// edge-incidence check look up arbitrary states, so the table is rebuilt from the (replicated) stored hashes.
+void ensure_full_table(am_handle *h)
+{
+    if (!h->table_sharded) return;
+    h->table_sharded = false;
+    const uint32_t before = h->tcap;
+    h->ensure_table((size_t)h->n_states);              // grows + rehashes everything if it was too small
+    if (h->tcap == before && h->n_states > 0) {
+        CK(cudaMemsetAsync(h->table.p, 0xFF, (size_t)h->tcap * 8, h->stream));
+        TableRef t{h->table.as<unsigned long long>(), h->tcap - 1};
+        rehash_kernel<<<(unsigned)((h->n_states + 255) / 256), 256, 0, h->stream>>>(h->hsum.as<unsigned long long>(),
+                                                                                     (int)h->n_states, t, 1, 0);
+        ++h->stats.n_launches;
+        CK(cudaGetLastError());
+    }
 }
 
 void resolve_spans(am_handle *h)
@@ -1515,6 +1616,13 @@ void am_destroy(am_handle *h)
         NcclApi::get().destroy(h->nccl_comm);
         h->nccl_comm = nullptr;
     }
+    if (h->xblock) {
+        cudaDeviceSynchronize();
+        for (int q = 0; q < h->xpeers.world; ++q)
+            if (q != h->xpeers.rank && h->xpeers.base[q]) cudaIpcCloseMemHandle(h->xpeers.base[q]);
+        cudaFree(h->xblock);
+        h->xblock = nullptr;
+    }
     h->free_all();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1570,6 +1678,58 @@ int am_set_shard_nccl(am_handle *h, int rank, int world, const void *unique_id12
     }
     h->shard_rank = rank;
     h->shard_world = world;
+    return AM_OK;
+}
+
+int am_set_shard_p2p(am_handle *h, int rank, int world, am_allgather_fn fn, void *user)
+{
+    if (!h) return AM_ERR_ARG;
+    if (world < 2 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world || !fn) {
+        h->err = "am_set_shard_p2p: need 0 <= rank < world, 2 <= world <= 16 and an all-gather callback";
+        return AM_ERR_ARG;
+    }
+    try {
+        if (h->xblock) throw CudaFail{"the exchange block of this handle is already set up"};
+        double mib = 96.0;
+        if (const char *e = getenv("AM_B200_XCHG_MIB")) mib = std::max(1.0, atof(e));
+        if (const char *e = getenv("AM_B200_XCHG_TIMEOUT_MS")) h->xtimeout_ns = (unsigned long long)(atof(e) * 1e6);
+        XchgLayout lay{};
+        lay.cap_corners = (int)std::min<double>(mib * (1 << 20) / 32.0, double(1 << 28));
+        lay.cap_states = lay.cap_corners / 3;
+        lay.region_bytes = (lay.xyz_off() + (size_t)lay.cap_corners * 24 + 255) & ~size_t(255);
+        lay.mask_cap = 1 << 22;
+        if (const char *e = getenv("AM_B200_XCHG_LEVEL_STATES")) lay.mask_cap = std::max(1024, atoi(e));
+        lay.mask_base = XCHG_CTRL_BYTES + (size_t)world * lay.region_bytes;
+        const size_t total = lay.mask_base + (size_t)world * lay.mask_cap * 4;
+        CK(cudaMalloc(&h->xblock, total));
+        CK(cudaMemset(h->xblock, 0, total));
+        CK(cudaDeviceSynchronize());
+        cudaIpcMemHandle_t mine;
+        CK(cudaIpcGetMemHandle(&mine, h->xblock));
+        std::vector<cudaIpcMemHandle_t> all(world);
+        if (fn(user, &mine, all.data(), (int64_t)sizeof(mine)) != 0) throw CudaFail{"the all-gather callback failed"};
+        XchgPeers p{};
+        p.world = world; p.rank = rank;
+        for (int q = 0; q < world; ++q) {
+            if (q == rank) { p.base[q] = static_cast<unsigned char *>(h->xblock); continue; }
+            void *ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess));
+            p.base[q] = static_cast<unsigned char *>(ptr);
+        }
+        // nobody may write into a block before its owner has zeroed it: one more round trip as a host barrier
+        std::vector<char> dummy(world * 8);
+        long long tag = rank;
+        if (fn(user, &tag, dummy.data(), 8) != 0) throw CudaFail{"the all-gather callback failed"};
+        h->xpeers = p;
+        h->xlay = lay;
+        h->xepoch = 0;
+        h->shard_rank = rank;
+        h->shard_world = world;
+        h->p2p = true;
+    } catch (const CudaFail &f) {
+        h->err = "am_set_shard_p2p: " + f.msg;
+        return f.code;
+    }
     return AM_OK;
 }
 
@@ -1647,6 +1807,7 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         CK(cudaMemsetAsync(h->counters.p, 0, CNT_NUM * 8, st));
         memset(h->h_counters, 0, CNT_NUM * 8);
         if (h->tcap) CK(cudaMemsetAsync(h->table.p, 0xFF, (size_t)h->tcap * 8, st));
+        h->table_sharded = h->p2p && h->shard_world > 1;
         insert_seeds(h, states, pts.data(), n_seeds);
         h->stats.n_seeds = n_seeds;
         h->stats.n_unique_seeds = h->n_states;
@@ -1698,6 +1859,7 @@ int am_combine(am_handle *h, double scale, const double center[3])
     }
     try {
         cudaStream_t st = h->stream;
+        ensure_full_table(h);
         const long long nC = h->stats.n_corners;
         const long long nS = h->n_states;
         DevBuf &owner = h->cmb_owner, &flag = h->cmb_flag, &vid = h->cmb_vid, &cvid = h->cmb_cvid, &verts = h->cmb_verts;
@@ -1943,6 +2105,7 @@ int am_edge_incidence(am_handle *h, int64_t out[4])
         acc.reserve(8 * 8);
         CK(cudaMemsetAsync(acc.p, 0, 8 * 8, st));
         const long long nS = h->n_states;
+        ensure_full_table(h);
         if (nS > 0) {
             StitchArgs sa{};
             sa.keys = h->keys.as<uint32_t>(); sa.hsum = h->hsum.as<unsigned long long>();

@@ -26,6 +26,7 @@ enum Counter {
     CNT_NEW,              // winners of the current level (scan total)
     CNT_CHUNK_CORNERS,    // corners of the current chunk (scan total)
     CNT_VERTS,            // unique vertices (combine)
+    CNT_XCHG_ERROR,       // sharded march: barrier time-outs (low 16 bits), bad records, inbox overflows (xchg.cuh)
     CNT_NUM
 };
 

@@ -88,7 +88,13 @@ struct LevelArgs {
     double *seedpt;
     uint8_t *owner;                       // sharded mode: rank that composes/clips the state (children inherit)
     int n_states;                         // states before this level's children are appended
+    // sharded visited set (xchg.cuh): a rank inserts only the candidates whose key hash it owns; the winners of
+    // all ranks arrive as one 32-bit mask per parent (bit j = edge slot j discovered a new state)
+    int world, rank;                      // world <= 1: single table, winners are read from the table
+    const uint32_t *wmask;
 };
+
+__device__ __forceinline__ int key_hash_owner(uint64_t h, int world) { return int(((h >> 32) * (uint64_t)world) >> 32); }
 
 // candidate (parent sid, edge slot j) <-> 31-bit index within the level
 __device__ __forceinline__ uint32_t cand_index(int s_local, int j) { return (uint32_t(s_local) << 5) | uint32_t(j); }
@@ -117,7 +123,8 @@ __global__ void expand_insert_kernel(const LevelArgs a)
                 const uint32_t fp = slot_fp(h);
                 const uint64_t mine = (uint64_t(fp) << 32) | CAND_TAG | cand_index(s, j);
                 uint32_t slot = uint32_t(h) & a.table.mask;
-                for (;;) {
+                const bool ours = (a.world <= 1) || key_hash_owner(h, a.world) == a.rank;
+                while (ours) {
                     unsigned long long v = 0;
                     if (tile.thread_rank() == 0) {
                         v = a.table.slots[slot];
@@ -194,11 +201,18 @@ __global__ void finalize_kernel(const LevelArgs a)
     const int k = int(a.face_off[sid + 1] - fo);
     const uint4 *key4 = reinterpret_cast<const uint4 *>(a.keys + (size_t)sid * a.kw);
     int nid = a.n_states + int(a.win_base[s]);
+    const uint32_t wm = a.wmask ? a.wmask[s] : 0u;
     for (int j = 0; j < k; ++j) {
         const int slot = a.cand_slot[(size_t)s * VSLOTS + j];
-        if (slot == NO_SLOT) continue;
-        const unsigned long long v = a.table.slots[slot];
-        if (uint32_t(v) != (CAND_TAG | cand_index(s, j))) continue;
+        unsigned long long v = 0;
+        if (a.wmask) {                      // winners of all ranks; `slot` is valid on the key's hash owner only
+            if (!((wm >> j) & 1u)) continue;
+            if (slot != NO_SLOT) v = a.table.slots[slot];
+        } else {
+            if (slot == NO_SLOT) continue;
+            v = a.table.slots[slot];
+            if (uint32_t(v) != (CAND_TAG | cand_index(s, j))) continue;
+        }
         const int e = a.face_edges[fo + j];
         uint4 *dst = reinterpret_cast<uint4 *>(a.keys_w + (size_t)nid * a.kw);
         for (int q = tile.thread_rank(); q < a.kw4; q += G) {
@@ -225,7 +239,7 @@ __global__ void finalize_kernel(const LevelArgs a)
             a.seedpt[(size_t)nid * 4 + 1] = my;
             a.seedpt[(size_t)nid * 4 + 2] = mz;
             a.seedpt[(size_t)nid * 4 + 3] = ext;
-            a.table.slots[slot] = (v & 0xFFFFFFFF00000000ull) | uint32_t(nid);
+            if (slot != NO_SLOT) a.table.slots[slot] = (v & 0xFFFFFFFF00000000ull) | uint32_t(nid);
         }
         ++nid;
     }
@@ -353,11 +367,12 @@ __global__ void hash_keys_kernel(const uint32_t *xkeys, int N, int kw, unsigned 
 }
 
 // rebuild the table from the stored hashes after it has grown (all stored keys are distinct)
-__global__ void rehash_kernel(const unsigned long long *hsum, int n, TableRef table)
+__global__ void rehash_kernel(const unsigned long long *hsum, int n, TableRef table, int world, int rank)
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n) return;
     const uint64_t h = hsum[id];
+    if (world > 1 && key_hash_owner(h, world) != rank) return;      // sharded visited set: another rank's key
     const unsigned long long mine = (uint64_t(slot_fp(h)) << 32) | uint32_t(id);
     uint32_t slot = uint32_t(h) & table.mask;
     while (atomicCAS(table.slots + slot, SLOT_EMPTY, mine) != SLOT_EMPTY) slot = (slot + 1) & table.mask;

@@ -1,0 +1,234 @@
+// xchg.cuh -- the per-level exchange of the sharded march over NVLink peer memory (no NCCL, no host in the loop).
+//
+// One march is spread over `world` GPUs, one process each (the reference has no multi-GPU path at
+// all, its only scale-out is the serial voxel loop of backend/main.py:475-556).  Compose + clip of a state run
+// on the rank that owns it; the key arena, the polygon CSR and the state numbering are replicated and stay
+// bit-identical on every rank; the visited set is sharded by key hash.  Two things cross the links per level:
+//
+//   polygons    the owner of a state PUSHES its polygon (edge ids + vertices, 28 B per corner, compacted) and a
+//               12-byte record {state, size, offset} into every peer's inbox with plain stores over NVLink;
+//               after one device-side barrier every rank scatters the sizes into state order, prefix-sums them
+//               and copies the polygons from its own inbox into the CSR -- the sizes and offsets never visit
+//               the host.  (Round 1: three ncclAllReduce over zero-padded buffers + a host sync per level.)
+//   winners     neighbour candidates are de-duplicated by the rank that owns the candidate key's hash (a rank
+//               probes / inserts only 1/world of the candidates into its shard of the visited set); the 32-bit
+//               mask "which edge slots of state s discovered a new state" is pushed to every peer and OR-ed
+//               after a second barrier.  4 B per state instead of the candidate keys: every rank can rebuild
+//               the winners' keys itself because it holds the parents' keys.
+//
+// Every rank owns ONE exchange block (cudaMalloc, exported with cudaIpcGetMemHandle, opened by the peers):
+//     [0, XCHG_CTRL_BYTES)         control: arrive[src] epoch flags (one 128-byte line per source rank)
+//     world polygon regions        region r is written by rank r only:
+//                                  header (64 B: number of records) | records [cap_states] | edges [cap_corners]
+//                                  | vertices [cap_corners][3]
+//     world mask regions           [mask_cap] uint32, region r written by rank r only
+// A region is reused every level: a rank writes level l+1 only after the barrier that follows level l's winner
+// exchange, which every rank reaches only after it has consumed level l's polygons (stream order).
+#pragma once
+#include "frontier.cuh"
+
+namespace amb {
+
+constexpr int XCHG_MAX_WORLD = 16;
+constexpr size_t XCHG_CTRL_BYTES = 4096;
+constexpr size_t XCHG_HDR_BYTES = 64;
+
+struct XchgPeers {
+    unsigned char *base[XCHG_MAX_WORLD];   // exchange block of every rank as mapped in THIS process (base[rank] = own)
+    int world, rank;
+};
+
+struct XchgLayout {
+    size_t region_bytes;      // one polygon region
+    size_t mask_base;         // offset of mask region 0
+    int cap_states;           // records per polygon region
+    int cap_corners;          // corners per polygon region
+    int mask_cap;             // states per mask region (= widest level the sharded march accepts)
+    __host__ __device__ size_t region(int r) const { return XCHG_CTRL_BYTES + (size_t)r * region_bytes; }
+    __host__ __device__ size_t rec_off() const { return XCHG_HDR_BYTES; }
+    __host__ __device__ size_t edge_off() const { return (XCHG_HDR_BYTES + (size_t)cap_states * 12 + 15) & ~size_t(15); }
+    __host__ __device__ size_t xyz_off() const { return (edge_off() + (size_t)cap_corners * 4 + 15) & ~size_t(15); }
+    __host__ __device__ size_t mask(int r) const { return mask_base + (size_t)r * mask_cap * 4; }
+};
+
+__device__ __forceinline__ unsigned long long xchg_now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Device-side barrier over all ranks: thread q announces `epoch` in rank q's block (release: everything this
+// rank wrote before -- earlier kernels of the stream included -- is visible to whoever observes the flag) and
+// waits until rank q has announced it here.  A peer that never arrives (crashed process) ends the wait after
+// timeout_ns and raises the error counter instead of hanging the GPU.
+__global__ void xchg_barrier_kernel(XchgPeers p, uint32_t epoch, unsigned long long timeout_ns, unsigned long long *counters)
+{
+    const int q = threadIdx.x;
+    if (q < p.world) {
+        __threadfence_system();
+        uint32_t *remote = reinterpret_cast<uint32_t *>(p.base[q]) + p.rank * 32;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+        const uint32_t *mine = reinterpret_cast<const uint32_t *>(p.base[p.rank]) + q * 32;
+        const unsigned long long t0 = xchg_now_ns();
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int32_t)(v - epoch) >= 0) break;
+            if (xchg_now_ns() - t0 > timeout_ns) {
+                atomicAdd(counters + CNT_XCHG_ERROR, 1ull);
+                break;
+            }
+            __nanosleep(64);
+        }
+        __threadfence_system();
+    }
+}
+
+// ---- polygons: owner -> every rank ------------------------------------------------------------------------
+struct XchgPackArgs {
+    const int *idx;           // the level-local indices of the states this rank owns (prefix of the permutation)
+    int n;                    // ... and their number
+    const int *cnt;           // clip output, stride VSLOTS per level-local state
+    const int *edges;
+    const double *verts;
+    int *cursor;              // device counter, zero at launch: corners packed so far
+    XchgPeers p;
+    XchgLayout lay;
+    unsigned long long *counters;
+};
+
+__global__ void xchg_pack_kernel(const XchgPackArgs a)
+{
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const size_t reg = a.lay.region(a.p.rank);
+    if (blockIdx.x == 0 && threadIdx.x < a.p.world)
+        *reinterpret_cast<int *>(a.p.base[threadIdx.x] + reg) = a.n;
+    if (i >= a.n) return;
+    const int s = a.idx[i];
+    int k = a.cnt[s];
+    int off = 0;
+    if (lane == 0 && k > 0) {
+        off = atomicAdd(a.cursor, k);
+        if (off + k > a.lay.cap_corners) {      // reported; the level is then incomplete and the march fails
+            atomicAdd(a.counters + CNT_XCHG_ERROR, 1ull << 32);
+            off = -1;
+        }
+    }
+    off = __shfl_sync(0xFFFFFFFFu, off, 0);
+    if (off < 0) k = 0, off = 0;
+    int e = 0;
+    double x = 0, y = 0, z = 0;
+    if (lane < k) {
+        e = a.edges[(size_t)s * VSLOTS + lane];
+        const double *v = a.verts + ((size_t)s * VSLOTS + lane) * 3;
+        x = v[0]; y = v[1]; z = v[2];
+    }
+    for (int q = 0; q < a.p.world; ++q) {
+        unsigned char *r = a.p.base[q] + reg;
+        if (lane == 0) {
+            int *rec = reinterpret_cast<int *>(r + a.lay.rec_off()) + (size_t)i * 3;
+            rec[0] = s; rec[1] = k; rec[2] = off;
+        }
+        if (lane < k) {
+            reinterpret_cast<int *>(r + a.lay.edge_off())[off + lane] = e;
+            double *o = reinterpret_cast<double *>(r + a.lay.xyz_off()) + (size_t)(off + lane) * 3;
+            o[0] = x; o[1] = y; o[2] = z;
+        }
+    }
+}
+
+// records of every source rank -> polygon size and location per level-local state (grid: x over records, y = source)
+__global__ void xchg_unpack_kernel(const unsigned char *own, XchgLayout lay, int S, int *cnt_all, int2 *where,
+                                   unsigned long long *counters)
+{
+    const int r = blockIdx.y;
+    const unsigned char *reg = own + lay.region(r);
+    const int n = *reinterpret_cast<const int *>(reg);
+    const int *rec = reinterpret_cast<const int *>(reg + lay.rec_off());
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int s = rec[(size_t)i * 3], k = rec[(size_t)i * 3 + 1], off = rec[(size_t)i * 3 + 2];
+        if (s < 0 || s >= S || k < 0 || k > VSLOTS) {
+            atomicAdd(counters + CNT_XCHG_ERROR, 1ull << 16);
+            continue;
+        }
+        cnt_all[s] = k;
+        where[s] = make_int2(r, off);
+    }
+}
+
+// own inbox -> global CSR, in state order (the sharded counterpart of compact_faces_kernel)
+struct XchgCompactArgs {
+    const unsigned char *own;
+    XchgLayout lay;
+    const int *cnt_all;
+    const uint32_t *off;          // exclusive scan of cnt_all
+    const int2 *where;
+    int S, sid0;
+    long long *face_off;
+    int *face_edges;
+    double *face_xyz;
+    unsigned long long *counters;
+};
+
+__global__ void xchg_compact_kernel(const XchgCompactArgs a)
+{
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (s >= a.S) return;
+    const long long base = (long long)a.counters[CNT_CORNERS] + a.off[s];
+    const int k = a.cnt_all[s];
+    if (lane == 0) {
+        a.face_off[a.sid0 + s] = base;
+        if (s == a.S - 1) a.face_off[a.sid0 + s + 1] = base + k;
+        if (k > 0) atomicAdd(a.counters + CNT_FACES, 1ull);
+    }
+    if (lane < k) {
+        const int2 w = a.where[s];
+        const unsigned char *reg = a.own + a.lay.region(w.x);
+        a.face_edges[base + lane] = reinterpret_cast<const int *>(reg + a.lay.edge_off())[w.y + lane];
+        const double *v = reinterpret_cast<const double *>(reg + a.lay.xyz_off()) + (size_t)(w.y + lane) * 3;
+        double *o = a.face_xyz + (size_t)(base + lane) * 3;
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    }
+}
+
+// ---- winners: hash owner -> every rank ----------------------------------------------------------------------
+// thread per parent state: bit j of the mask = candidate (s, j) was inserted by THIS rank and won its slot
+__global__ void xchg_push_masks_kernel(const LevelArgs a, XchgPeers p, XchgLayout lay)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.S) return;
+    uint32_t m = 0;
+    for (int j = 0; j < VSLOTS; ++j) {
+        const int slot = a.cand_slot[(size_t)s * VSLOTS + j];
+        if (slot != NO_SLOT && uint32_t(a.table.slots[slot]) == (CAND_TAG | cand_index(s, j))) m |= 1u << j;
+    }
+    const size_t off = lay.mask(p.rank);
+    for (int q = 0; q < p.world; ++q) reinterpret_cast<uint32_t *>(p.base[q] + off)[s] = m;
+}
+
+// OR of the masks of all ranks -> winners per parent (+ the bucket histogram of the children this rank will
+// compose, exactly as count_winners_kernel does on a single GPU)
+__global__ void xchg_merge_masks_kernel(const LevelArgs a, const unsigned char *own, XchgLayout lay, int world,
+                                        uint32_t *wmask, LayerOffs lo, int *next_counts, int rank)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.S) return;
+    uint32_t m = 0;
+    for (int r = 0; r < world; ++r) m |= reinterpret_cast<const uint32_t *>(own + lay.mask(r))[s];
+    wmask[s] = m;
+    a.nwin[s] = __popc(m);
+    if (m && a.owner[a.lb + s] == rank) {
+        const long long fo = a.face_off[a.lb + s];
+        for (uint32_t t = m; t; t &= t - 1) {
+            const int e = a.face_edges[fo + (__ffs(t) - 1)];
+            int b = 1;
+            while (b < lo.D && e >= lo.off[b + 1]) ++b;
+            atomicAdd(next_counts + b, 1);
+        }
+    }
+}
+
+}  // namespace amb

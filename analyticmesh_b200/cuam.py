@@ -38,7 +38,7 @@ class AmStats(ctypes.Structure):
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",
            "am_key_words", "am_state_len", "am_copy_states", "am_copy_faces", "am_copy_mesh", "am_load_weights",
            "am_debug_planes", "am_compose_profile", "am_kernel_profile", "am_gemm_variant", "am_fp64_peak_tflops", "am_set_shard", "am_nccl_unique_id",
-           "am_set_shard_nccl", "am_gather_states", "am_digest", "am_edge_incidence", "am_ply_parse_faces",
+           "am_set_shard_nccl", "am_set_shard_p2p", "am_gather_states", "am_digest", "am_edge_incidence", "am_ply_parse_faces",
            "am_ply_pack_faces")
 
 
@@ -355,6 +355,32 @@ def set_shard_nccl(rank, world, broadcast_bytes):
     fn = lib().am_set_shard_nccl
     fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
     _err(fn(_handle, int(rank), int(world), uid), "set_shard_nccl")
+
+
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+_gather_cb = None
+
+
+def set_shard_p2p(rank, world, allgather):
+    """Spread ONE march over `world` processes (one GPU each) with the engine's own exchange over NVLink peer
+    memory (include/am_b200.h: am_set_shard_p2p).  `allgather(payload: bytes) -> list[bytes]` (rank order) is
+    used during set-up only, to swap the CUDA IPC handles (analyticmesh_b200.parallel.make_allgather)."""
+    global _gather_cb
+
+    def _cb(_user, send, recv, nbytes):
+        try:
+            parts = allgather(ctypes.string_at(send, nbytes))
+            assert len(parts) == world and all(len(b) == nbytes for b in parts)
+            ctypes.memmove(recv, b"".join(parts), nbytes * world)
+            return 0
+        except Exception as e:  # noqa: BLE001 - reported through the C ABI as a failed callback
+            print(f"(cuam) all-gather callback failed: {e!r}")
+            return 1
+
+    _gather_cb = ALLGATHER_FN(_cb)
+    fn = lib().am_set_shard_p2p
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    _err(fn(_handle, int(rank), int(world), ctypes.cast(_gather_cb, ctypes.c_void_p), None), "set_shard_p2p")
 
 
 def fp64_peak_tflops():

@@ -1,5 +1,7 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the one exchange
-step of the sharded march (include/am_b200.h: am_set_shard).
+"""Multi-GPU plumbing: one process per GPU.  The default sharded march (include/am_b200.h: am_set_shard_p2p)
+exchanges polygons and winner masks with the engine's own kernels over NVLink peer memory; torch.distributed
+is only used to swap the CUDA IPC handles at set-up (make_allgather).  The round-1 scheme (am_set_shard /
+am_set_shard_nccl: all-reduce of the level's polygons) is kept as a cross-check.
 
 Per BFS level every rank clips the states it owns; the level's polygon scratch is zero in every slot
 a rank does not own, so an integer all-reduce(SUM) over the int32 view of the buffer is the exact
@@ -58,3 +60,16 @@ def broadcast_bytes(payload, group=None, device=None):
         t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
     dist.broadcast(t, src=0, group=group)
     return bytes(t.cpu().numpy().tobytes())
+
+
+def make_allgather(group=None, device=None):
+    """Returns allgather(payload: bytes) -> list[bytes] over the ranks of `group` (rank order), for
+    cuam.set_shard_p2p.  device None: cuda tensors with NCCL, cpu tensors with gloo."""
+    def allgather(payload):
+        dev = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+        mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+        parts = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, mine, group=group)
+        return [bytes(p.cpu().numpy().tobytes()) for p in parts]
+
+    return allgather

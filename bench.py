@@ -222,9 +222,13 @@ def main():
     cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table, num_extra_constraints=0)
     torch.cuda.synchronize()
     init_cuda_time = time.time() - t0
+    shard_mode = os.environ.get("AM_B200_SHARD", "p2p")
     if world > 1:
-        from analyticmesh_b200.parallel import broadcast_bytes
-        cuam.set_shard_nccl(rank, world, lambda b: broadcast_bytes(b, device=dev))
+        from analyticmesh_b200.parallel import broadcast_bytes, make_allgather
+        if shard_mode == "nccl":      # round-1 scheme: ncclAllReduce of the level's polygons, replicated visited set
+            cuam.set_shard_nccl(rank, world, lambda b: broadcast_bytes(b, device=dev))
+        else:                         # the engine's own exchange over NVLink peer memory (csrc/xchg.cuh)
+            cuam.set_shard_p2p(rank, world, make_allgather(device=dev))
 
     def barrier():
         if world > 1:
@@ -348,8 +352,13 @@ def main():
                        "states_per_step_rank0": last["n_states"], "bfs_levels": last["n_levels"],
                        "l2_note": "every step streams >= 9 GB of keys and >100 GB of plane rows through a 126 MB L2; "
                                   "inputs are far larger than L2, no flush needed",
-                       "parallelism": f"1 process per GPU; compose+clip sharded by state owner over {world} GPUs, one NCCL "
-                                      "all-reduce of the level's polygons per BFS level, frontier replicated"
+                       "parallelism": (f"1 process per GPU; compose+clip sharded by state owner over {world} GPUs, visited set "
+                                       "sharded by key hash; per BFS level the polygons and winner masks are pushed into the "
+                                       "peers' inboxes over NVLink by the engine's kernels (CUDA IPC peer memory, device-side "
+                                       "flag barriers, no host sync, no NCCL); key arena + CSR replicated"
+                                       if shard_mode != "nccl" else
+                                       f"1 process per GPU; compose+clip sharded over {world} GPUs, ncclAllReduce of the level's "
+                                       "polygons, frontier replicated (round-1 scheme)")
                        if world > 1 else "single GPU",
                        "mesh_time_s": {"init_point_time": init_point_time, "init_cuda_time": init_cuda_time,
                                        "am_time": dt / args.steps,

@@ -105,6 +105,15 @@ int am_set_shard(am_handle *h, int rank, int world, am_allreduce_fn fn, void *us
 int am_nccl_unique_id(void *out128);
 int am_set_shard_nccl(am_handle *h, int rank, int world, const void *unique_id128);
 
+/* Same march, with the per-level exchange done by the engine's own kernels over NVLink peer memory
+ * (csrc/xchg.cuh): every rank allocates one exchange block, the blocks are mapped into all processes with CUDA
+ * IPC, polygons and winner masks are pushed with plain stores and ordered by device-side flag barriers; the
+ * visited set is sharded by key hash.  No collective library and no host synchronisation inside a level.
+ * `fn` is only used here, during set-up: it must gather `bytes` bytes from every rank into recv (rank order)
+ * on every rank, e.g. torch.distributed.all_gather, and return 0.  Collective call. */
+typedef int (*am_allgather_fn)(void *user, const void *send, void *recv, int64_t bytes);
+int am_set_shard_p2p(am_handle *h, int rank, int world, am_allgather_fn fn, void *user);
+
 int am_get_stats(const am_handle *h, am_stats *out);
 const char *am_last_error(const am_handle *h);   /* h may be NULL: error of the last failed am_create */
 int am_key_words(const am_handle *h);            /* 32-bit words per stored key (multiple of 4) */

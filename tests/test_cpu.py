@@ -283,7 +283,15 @@ def _gloo_worker(rank, world, port, q):
     buf[mine] = (np.arange(n, dtype=np.int64)[mine] * 2654435761 % 2**31).astype(np.int32)
     make_allreduce(device="cpu")(buf.ctypes.data, n)
     expect = (np.arange(n, dtype=np.int64) * 2654435761 % 2**31).astype(np.int32)
-    q.put((rank, bool(np.array_equal(buf, expect))))
+    # the handle swap of the peer-memory exchange (cuam.set_shard_p2p): 64-byte payloads, rank order on every rank
+    from analyticmesh_b200.parallel import make_allgather
+    parts = make_allgather(device="cpu")(bytes([rank + 1]) * 64)
+    gathered = parts == [bytes([r + 1]) * 64 for r in range(world)]
+    # hash ownership of the sharded visited set (csrc/frontier.cuh key_hash_owner): a partition of the key space
+    hs = np.random.RandomState(7).randint(0, 2**63, 10000).astype(np.uint64) * np.uint64(2) + np.uint64(rank)
+    own = ((hs >> np.uint64(32)) * np.uint64(world)) >> np.uint64(32)
+    balanced = bool(own.min() == 0 and own.max() == world - 1 and abs(float((own == 0).mean()) - 1.0 / world) < 0.05)
+    q.put((rank, bool(np.array_equal(buf, expect)) and gathered and balanced))
     dist.destroy_process_group()
 
 

@@ -121,6 +121,20 @@ def _torchrun(n, script, *args, timeout=900):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
 
 
+def test_sharded_march_two_ranks_sharing_one_gpu():
+    """The multi-rank code path on a single-GPU box: two processes time-slice cuda:0, map each other's exchange
+    block with CUDA IPC and run the same device-side barriers / peer pushes as over NVLink (csrc/xchg.cuh).
+    Bit-identical to the unsharded march on a DMMA-path and a tcgen05-path network."""
+    env = dict(os.environ, AM_SHARD_SAME_GPU="1", AM_B200_XCHG_TIMEOUT_MS="15000", AM_B200_XCHG_MIB="16",
+               AM_B200_RESIDENT_GIB="8")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29537", os.path.join(ROOT, "tools/shard_check.py"), "chair_cube", "mlp3x256s_cube", "skipnet"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if "identical=" in ln]
+    assert len(lines) == 3 and all("identical=True" in ln for ln in lines), lines
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_sharded_march_is_bit_identical_to_single_gpu():
     """One march spread over all visible GPUs == the single-GPU march: keys, numbering, polygons, stitched mesh

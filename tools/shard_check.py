@@ -1,5 +1,10 @@
-"""Sharded march == single-GPU march, bit for bit.  Launch with
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/shard_check.py [case ...]"""
+"""Sharded march == single-GPU march, bit for bit (keys, numbering, polygons, stitched mesh).  Launch with
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+       tools/shard_check.py [case ...]
+Modes compared with the unsharded march: the exchange over NVLink peer memory (am_set_shard_p2p, the default
+of bench.py) and -- on distinct GPUs -- the two all-reduce schemes of round 1 (am_set_shard_nccl / am_set_shard).
+AM_SHARD_SAME_GPU=1: every rank uses cuda:0 (two processes time-slicing one GPU, CUDA IPC between them, gloo for
+the handle swap) so that the multi-rank code path is exercised on a single-GPU box as well."""
 import hashlib
 import os
 import sys
@@ -10,13 +15,17 @@ import torch
 import torch.distributed as dist
 
 from analyticmesh_b200 import cuam
-from analyticmesh_b200.parallel import make_allreduce
+from analyticmesh_b200.parallel import broadcast_bytes, make_allgather, make_allreduce
 from tests.golden.cases import build_case
-from tests import parity
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+same_gpu = os.environ.get("AM_SHARD_SAME_GPU", "0") == "1"
+torch.cuda.set_device(0 if same_gpu else local)
+if same_gpu:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+modes = [("p2p", 3)] if same_gpu else [("p2p", 3), ("nccl", 2), ("callback", 1)]
 for name in (sys.argv[1:] or ["chair_cube", "skipnet", "chair", "mlp4x128s"]):
     case = build_case(name)
 
@@ -27,29 +36,38 @@ for name in (sys.argv[1:] or ["chair_cube", "skipnet", "chair", "mlp4x128s"]):
         if shard == 1:
             cuam.set_shard(rank, world, make_allreduce())
         elif shard == 2:
-            from analyticmesh_b200.parallel import broadcast_bytes
             cuam.set_shard_nccl(rank, world, broadcast_bytes)
+        elif shard == 3:
+            cuam.set_shard_p2p(rank, world, make_allgather())
         cuam.AnalyticMarching(weights=info.weights, biases=info.biases, states=case["states"], points=case["points"],
                               arc_tm=info.arc_tm, w_extra_constraints=case["w_extra"].reshape(-1, 3),
                               b_extra_constraints=case["b_extra"].reshape(-1), iso=0.0, flip_insideout=False)
         keys, fo, par, via = cuam.states()
         e, v = cuam.faces()
         st = cuam.stats()
+        dev_digest = cuam.digest()["ordered"]
         cuam.CombineMesh(1.0, [0, 0, 0])
         mv, fs, fi = cuam.mesh()
+        inc = cuam.edge_incidence()
         h = hashlib.sha256()
         for a in (keys, fo, par, via, e, v, mv, fs, fi):
             h.update(np.ascontiguousarray(a).tobytes())
-        return h.hexdigest(), st
+        h.update(repr(sorted(inc.items())).encode())
+        return h.hexdigest() + dev_digest, st
 
-    d1, s1 = digest(0)
-    d2, s2 = digest(2)
-    d3, s3 = digest(1)
-    ok = d1 == d2 == d3
-    t = torch.tensor([int(ok)], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    d0, s0 = digest(0)
+    ok, times = True, []
+    for label, m in modes:
+        d, s = digest(m)
+        ok = ok and (d == d0)
+        times.append(f"t_{label}={s['seconds_march']:.4f}s")
+    flag = torch.tensor([int(ok)])
+    if not same_gpu:
+        flag = flag.cuda()
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"{name}: world={world} identical={bool(t.item())} faces={s2['n_faces']} "
-              f"t_single={s1['seconds_march']:.4f}s t_sharded={s2['seconds_march']:.4f}s", flush=True)
+        print(f"{name}: world={world} identical={bool(flag.item())} faces={s0['n_faces']} "
+              f"t_single={s0['seconds_march']:.4f}s " + " ".join(times), flush=True)
     assert ok, (name, rank)
+cuam.Destroy()
 dist.destroy_process_group()
