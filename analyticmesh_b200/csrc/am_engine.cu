@@ -11,6 +11,7 @@
 //                       expand + insert (frontier.cuh phase 1), count winners, scan,
 //                       -> read back n_new, grow arenas, finalize (phase 2)
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -409,6 +410,10 @@ struct am_handle {
     uint32_t xepoch = 0;
     unsigned long long xtimeout_ns = 20000000000ull;
     DevBuf xcursor, xcnt, xwhere, wmask;
+    DevBuf bal_loads, bal_cuts;                 // load balance of the sharded march (xchg.cuh winners_scan_kernel)
+    bool balance = true;
+    DevBuf level_cursor;                        // [D + 3] bucket cursors of classify_scatter_kernel, zero between levels
+    DevBuf fs_sums, fs_off, fs_sums2, fs_off2, fs_ticket;   // fused scans (scan.cuh): CSR offsets / new state ids
     bool table_sharded = false;                 // the visited set holds only the keys whose hash this rank owns
     int *h_npre = nullptr;                      // pinned
     int *h_next = nullptr;                      // pinned: bucket histogram of the NEXT level (count_winners_kernel)
@@ -426,7 +431,10 @@ struct am_handle {
     double gemm_ms = 0.0, gemm_flops = 0.0;
     long long gemm_launches = 0;
     // span kinds: 0 composition chain of a chunk, 1 compose phase, 2 clip, 3 frontier, 4 tensor GEMM kernel, 5 digit kernel
-    static constexpr int N_KINDS = 8;
+    // 6 exchange barriers (time waiting for the slowest rank), 7 polygon push, 8 unpack + scan + CSR, 9 neighbour
+    // enumeration + visited-set insert, 10 winner masks / count, 11 finalize
+    static constexpr int N_KINDS = 12;
+    double host_wait_s = 0.0, host_level_s = 0.0;      // host wall time blocked in the per-level sync / spent per level
     double kind_ms[N_KINDS] = {}, kind_flops[N_KINDS] = {};
     long long kind_launches[N_KINDS] = {};
     std::vector<cudaEvent_t> ev_pool;
@@ -468,7 +476,8 @@ struct am_handle {
                          &table, &planes, &equ, &f_cnt, &f_off, &f_edges, &f_verts, &cand_slot, &nwin, &wbase, &scan_a,
                          &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates, &lvl_planes[0], &lvl_planes[1],
                          &bucket, &perm, &bcounts, &owner, &xchg, &cmb_owner, &cmb_flag, &cmb_vid, &cmb_cvid, &cmb_verts,
-                         &digest_acc, &xcursor, &xcnt, &xwhere, &wmask};
+                         &digest_acc, &xcursor, &xcnt, &xwhere, &wmask,
+                         &level_cursor, &fs_sums, &fs_off, &fs_sums2, &fs_off2, &fs_ticket, &bal_loads, &bal_cuts};
         for (DevBuf *b : all) b->release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear();
@@ -581,6 +590,20 @@ struct am_handle {
         scan_apply_kernel<<<nb, SCAN_THREADS, 0, stream>>>(in, n, scan_b.as<uint32_t>(), out, total_dev);
         ++stats.n_launches;
         CK(cudaGetLastError());
+    }
+
+    // fused scan descriptor (scan.cuh) for n items; which = 0: CSR offsets, 1: new state ids
+    FusedScan fused_scan(int n, int which, unsigned long long *total)
+    {
+        const size_t nb = (size_t)(n + FS_TILE - 1) / FS_TILE + 1;
+        DevBuf &sums = which ? fs_sums2 : fs_sums, &offs = which ? fs_off2 : fs_off;
+        sums.reserve(nb * 4, 0, false);
+        offs.reserve(nb * 4, 0, false);
+        FusedScan fs{};
+        fs.block_sums = sums.as<uint32_t>(); fs.block_off = offs.as<uint32_t>();
+        fs.ticket = fs_ticket.as<unsigned int>() + which; fs.total = total;
+        fs.bump_dst = nullptr; fs.bump_src = nullptr;
+        return fs;
     }
 
     // ---------------- composition of one chunk: keys of states [sid0, sid0+Sc) -------------------
@@ -1162,12 +1185,31 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
 // does not own), every rank then knows the level's CSR offsets, writes only its own polygons into the
 // zeroed CSR range, and the range is summed over the ranks: 4 + 28 B per corner cross NVLink instead of
 // the fixed-stride scratch.
-void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc)
+void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc, bool fused = false)
 {
     cudaStream_t st = h->stream;
     unsigned long long *cnt = h->counters.as<unsigned long long>();
     const bool sharded = h->shard_world > 1;
     h->f_off.reserve((size_t)Sc * 4, 0, false);
+    if (fused && !sharded) {
+        // one launch scans the polygon sizes (block-local prefix + block offsets), one copies the polygons; the
+        // running corner total is advanced by the level's winner kernel (process_level)
+        FusedScan fs = h->fused_scan(Sc, 0, cnt + CNT_CHUNK_CORNERS);
+        scan_local_kernel<<<(Sc + FS_TILE - 1) / FS_TILE, FS_THREADS, 0, st>>>(reinterpret_cast<uint32_t *>(sc.cnt), Sc,
+                                                                             h->f_off.as<uint32_t>(), fs);
+        ++h->stats.n_launches;
+        CompactArgs co{};
+        co.owner = nullptr; co.rank = 0;
+        co.cnt = sc.cnt; co.off = h->f_off.as<uint32_t>(); co.block_off = fs.block_off;
+        co.edges = sc.edges; co.verts = sc.verts;
+        co.S = Sc; co.sid0 = (int)sid0;
+        co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
+        co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
+        compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
+        ++h->stats.n_launches;
+        CK(cudaGetLastError());
+        return;
+    }
     if (sharded) h->allreduce_i32(sc.cnt, Sc);
     h->scan(reinterpret_cast<uint32_t *>(sc.cnt), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
     long long base = 0, n_lvl = 0;
@@ -1184,7 +1226,7 @@ void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc)
     CompactArgs co{};
     co.owner = sharded ? h->owner.as<uint8_t>() : nullptr;
     co.rank = h->shard_rank;
-    co.cnt = sc.cnt; co.off = h->f_off.as<uint32_t>();
+    co.cnt = sc.cnt; co.off = h->f_off.as<uint32_t>(); co.block_off = nullptr;
     co.edges = sc.edges; co.verts = sc.verts;
     co.S = Sc; co.sid0 = (int)sid0;
     co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
@@ -1206,7 +1248,11 @@ void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc)
 void xchg_barrier(am_handle *h)
 {
     ++h->xepoch;
+    const bool t = h->timing_on();
+    size_t e0 = 0;
+    if (t) e0 = h->span_begin();
     xchg_barrier_kernel<<<1, 32, 0, h->stream>>>(h->xpeers, h->xepoch, h->xtimeout_ns, h->counters.as<unsigned long long>());
+    if (t) h->span_end(e0, 6);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
 }
@@ -1222,27 +1268,33 @@ void store_faces_p2p(am_handle *h, long long sid0, int Sc, Scratch sc, const int
     h->xcnt.reserve((size_t)Sc * 4, 0, false);
     h->xwhere.reserve((size_t)Sc * 8, 0, false);
     h->f_off.reserve((size_t)Sc * 4, 0, false);
-    CK(cudaMemsetAsync(h->xcursor.p, 0, 4, st));
-    XchgPackArgs pa{};
+    XchgPackArgs pa{};      // the cursor is zero: cleared by the previous level's winner kernel
     pa.idx = idx; pa.n = n_mine; pa.cnt = sc.cnt; pa.edges = sc.edges; pa.verts = sc.verts;
     pa.cursor = h->xcursor.as<int>(); pa.p = h->xpeers; pa.lay = h->xlay; pa.counters = cnt;
+    const bool tm = h->timing_on();
+    size_t e0 = 0;
+    if (tm) e0 = h->span_begin();
     xchg_pack_kernel<<<(unsigned)std::max(1, (n_mine + 7) / 8), 256, 0, st>>>(pa);
+    if (tm) h->span_end(e0, 7);
     ++h->stats.n_launches;
     xchg_barrier(h);
+    if (tm) e0 = h->span_begin();
     const unsigned char *own = h->xpeers.base[h->shard_rank];
     dim3 ug((unsigned)std::max(1, std::min((Sc + 255) / 256, 64)), (unsigned)h->shard_world);
     xchg_unpack_kernel<<<ug, 256, 0, st>>>(own, h->xlay, Sc, h->xcnt.as<int>(), h->xwhere.as<int2>(), cnt);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
-    h->scan(h->xcnt.as<uint32_t>(), h->f_off.as<uint32_t>(), Sc, cnt + CNT_CHUNK_CORNERS);
+    FusedScan fs = h->fused_scan(Sc, 0, cnt + CNT_CHUNK_CORNERS);
+    scan_local_kernel<<<(Sc + FS_TILE - 1) / FS_TILE, FS_THREADS, 0, st>>>(h->xcnt.as<uint32_t>(), Sc, h->f_off.as<uint32_t>(), fs);
+    ++h->stats.n_launches;
     XchgCompactArgs co{};
     co.own = own; co.lay = h->xlay; co.cnt_all = h->xcnt.as<int>(); co.off = h->f_off.as<uint32_t>();
+    co.block_off = fs.block_off;
     co.where = h->xwhere.as<int2>(); co.S = Sc; co.sid0 = (int)sid0;
     co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
     co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
     xchg_compact_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
-    ++h->stats.n_launches;
-    bump_counters_kernel<<<1, 32, 0, st>>>(cnt);
+    if (tm) h->span_end(e0, 8);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
 }
@@ -1281,23 +1333,12 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         h->perm.reserve((size_t)S * 4, 0, false);
         h->bcounts.reserve((size_t)3 * (D + 3) * 4, 0, false);
         int *counts = h->bcounts.as<int>(), *cursor = counts + (D + 3), *npre_d = counts + 2 * (D + 3);
-        CK(cudaMemsetAsync(counts, 0, (size_t)(D + 3) * 4, st));
         LayerOffs lo{};
         lo.D = D;
         for (int l = 1; l <= D + 1; ++l) lo.off[l] = h->off[l];
         const unsigned sb = (unsigned)((S + 255) / 256);
-        classify_kernel<<<sb, 256, 0, st>>>(h->via.as<int>(), h->parent.as<int>(), (int)lb, (int)S,
-                                            h->prev_resident ? (int)h->prev_lb : 0, h->prev_resident ? (int)h->prev_S : 0,
-                                            lo, h->bucket.as<int>(), counts, sharded ? h->owner.as<uint8_t>() : nullptr,
-                                            h->shard_rank);
-        ++h->stats.n_launches;
-        bucket_offsets_kernel<<<1, 32, 0, st>>>(counts, cursor, npre_d, D);
-        ++h->stats.n_launches;
-        scatter_kernel<<<sb, 256, 0, st>>>(h->bucket.as<int>(), (int)S, cursor, h->perm.as<int>());
-        ++h->stats.n_launches;
-        CK(cudaGetLastError());
         std::vector<int> npre(D + 3, 0);
-        // launch sizes of this level: predicted by count_winners_kernel of the previous level (read back
+        // launch sizes of this level: predicted by the winner kernel of the previous level (read back
         // together with n_new), computed for the seed level, or -- fallback -- read back now
         bool have = false;
         if (lb == 0) {                       // seeds: every state is recomputed from layer 2 on
@@ -1316,6 +1357,28 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
             npre[D + 1] = (int)S;
             have = true;
         }
+        if (have) {      // bucket sizes known: classify + scatter in one launch, bucket starts as launch parameters
+            BucketBase bb{};
+            for (int b = 1; b <= D + 1; ++b) bb.base[b] = npre[b - 1];
+            classify_scatter_kernel<<<sb, 256, 0, st>>>(h->via.as<int>(), h->parent.as<int>(), (int)lb, (int)S,
+                                                        h->prev_resident ? (int)h->prev_lb : 0,
+                                                        h->prev_resident ? (int)h->prev_S : 0, lo, bb, h->bucket.as<int>(),
+                                                        h->level_cursor.as<int>(), h->perm.as<int>(),
+                                                        sharded ? h->owner.as<uint8_t>() : nullptr, h->shard_rank);
+            ++h->stats.n_launches;
+        } else {
+            CK(cudaMemsetAsync(counts, 0, (size_t)(D + 3) * 4, st));
+            classify_kernel<<<sb, 256, 0, st>>>(h->via.as<int>(), h->parent.as<int>(), (int)lb, (int)S,
+                                                h->prev_resident ? (int)h->prev_lb : 0, h->prev_resident ? (int)h->prev_S : 0,
+                                                lo, h->bucket.as<int>(), counts, sharded ? h->owner.as<uint8_t>() : nullptr,
+                                                h->shard_rank);
+            ++h->stats.n_launches;
+            bucket_offsets_kernel<<<1, 32, 0, st>>>(counts, cursor, npre_d, D);
+            ++h->stats.n_launches;
+            scatter_kernel<<<sb, 256, 0, st>>>(h->bucket.as<int>(), (int)S, cursor, h->perm.as<int>());
+            ++h->stats.n_launches;
+        }
+        CK(cudaGetLastError());
         if (!have) CK(cudaMemcpyAsync(h->h_npre, npre_d, (size_t)(D + 2) * 4, cudaMemcpyDeviceToHost, st));
         if (sharded && !h->p2p) CK(cudaMemsetAsync(sc.cnt, 0, (size_t)S * 4, st));   // counts of states owned elsewhere
         h->lazy_prev = nullptr;
@@ -1342,7 +1405,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         if (timing) t0 = h->span_begin();
         run_clip(h, lb, sharded ? n_mine : (int)S, base, flip, sharded ? h->perm.as<int>() : nullptr, sc);
         if (sharded && h->p2p) store_faces_p2p(h, lb, (int)S, sc, h->perm.as<int>(), n_mine);   // NVLink peer pushes
-        else store_faces(h, lb, (int)S, sc);   // sharded: + the level's collectives (sizes, edges, vertices)
+        else store_faces(h, lb, (int)S, sc, /*fused=*/!sharded);   // sharded (NCCL scheme): + the level's collectives
         h->lazy_prev = nullptr;
         if (timing) h->span_end(t0, 2);
         h->prev_resident = true;
@@ -1377,6 +1440,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     }
 
     // ---- neighbour enumeration + visited set ----------------------------------------------------
+    const bool fused_faces = resident && (h->shard_world == 1 || h->p2p);   // corner total advanced by the winner kernel
     size_t t0 = 0;
     const bool timing = h->timing_on();
     if (timing) t0 = h->span_begin();
@@ -1400,7 +1464,10 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     a.wmask = nullptr;
     if (p2p && S > h->xlay.mask_cap)
         throw CapacityFail{"sharded march: a BFS level of " + std::to_string(S) + " states exceeds the winner-mask region"};
+    size_t tk = 0;
+    if (timing) tk = h->span_begin();
     h->dispatch_group([&](auto g) { expand_insert_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
+    if (timing) h->span_end(tk, 9);
     ++h->stats.n_launches;
     {
         LayerOffs lo{};
@@ -1408,24 +1475,48 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         for (int l = 1; l <= h->D + 1; ++l) lo.off[l] = h->off[l];
         a.owner = h->shard_world > 1 ? h->owner.as<uint8_t>() : nullptr;
         CK(cudaMemsetAsync(h->next_counts.p, 0, (size_t)(h->D + 3) * 4, st));
+        // winners per parent + bucket histogram of the children + the prefix sums that number them: one launch
+        // (xchg.cuh winners_scan_kernel).  It also advances the running corner total of the fused CSR path, clears
+        // the small cursors of the next level's kernels and, in sharded mode, deals the free children to the ranks.
+        h->wmask.reserve((size_t)S * 4, 0, false);
+        h->wbase.reserve((size_t)S * 8, 0, false);
+        const size_t nb = (size_t)(S + FS_TILE - 1) / FS_TILE + 1;
+        h->fs_sums2.reserve(nb * 8, 0, false);
+        h->fs_off2.reserve(nb * 8, 0, false);
+        WinArgs w{};
+        w.lo = lo; w.next_counts = h->next_counts.as<int>(); w.rank = h->shard_rank; w.world = h->shard_world;
+        w.wmask = h->wmask.as<uint32_t>(); w.win_base = h->wbase.as<unsigned long long>();
+        w.fs.block_sums = h->fs_sums2.as<unsigned long long>(); w.fs.block_off = h->fs_off2.as<unsigned long long>();
+        w.fs.ticket = h->fs_ticket.as<unsigned int>() + 1; w.fs.total = cnt + CNT_NEW;
+        w.fs.bump_dst = fused_faces ? cnt + CNT_CORNERS : nullptr; w.fs.bump_src = cnt + CNT_CHUNK_CORNERS;
+        w.zero_a = h->level_cursor.as<int>(); w.n_zero_a = h->D + 3; w.zero_b = h->xcursor.as<int>();
+        w.own = p2p ? h->xpeers.base[h->shard_rank] : nullptr; w.lay = h->xlay;
+        w.balance = (h->shard_world > 1 && h->balance) ? 1 : 0;
+        w.loads = h->bal_loads.as<unsigned long long>(); w.cuts = h->bal_cuts.as<int>();
+        w.unit_clip = 3;
+        const unsigned wb = (unsigned)((S + FS_TILE - 1) / FS_TILE);
         if (p2p) {   // winners of the candidates whose hash this rank owns -> every rank; OR after the barrier
-            h->wmask.reserve((size_t)S * 4, 0, false);
             xchg_push_masks_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a, h->xpeers, h->xlay);
             ++h->stats.n_launches;
             xchg_barrier(h);
-            xchg_merge_masks_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(
-                a, h->xpeers.base[h->shard_rank], h->xlay, h->shard_world, h->wmask.as<uint32_t>(), lo,
-                h->next_counts.as<int>(), h->shard_rank);
-            a.wmask = h->wmask.as<uint32_t>();
+            winners_scan_kernel<true><<<wb, FS_THREADS, 0, st>>>(a, w);
         } else {
-            count_winners_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a, lo, h->next_counts.as<int>(), h->shard_rank);
+            winners_scan_kernel<false><<<wb, FS_THREADS, 0, st>>>(a, w);
         }
+        a.wmask = w.wmask;
+        a.win_base64 = w.win_base; a.win_off64 = w.fs.block_off;
+        a.cuts = w.balance ? w.cuts : nullptr;
+        a.free_below_bit = h->off[2 <= h->D ? 2 : h->D + 1];
+        a.n_ranks = h->shard_world;
         ++h->stats.n_launches;
         CK(cudaGetLastError());
     }
-    h->scan(h->nwin.as<uint32_t>(), h->wbase.as<uint32_t>(), (int)S, cnt + CNT_NEW);
     CK(cudaMemcpyAsync(h->h_next, h->next_counts.p, (size_t)(h->D + 3) * 4, cudaMemcpyDeviceToHost, st));
-    h->read_counters();                                   // the one host sync of the level
+    {
+        const auto w0 = std::chrono::steady_clock::now();
+        h->read_counters();                               // the one host sync of the level
+        h->host_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+    }
     h->next_valid = true;
     if (h->h_counters[CNT_XCHG_ERROR] != 0) {
         const unsigned long long e = h->h_counters[CNT_XCHG_ERROR];
@@ -1443,7 +1534,9 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     a.owner = h->shard_world > 1 ? h->owner.as<uint8_t>() : nullptr;
     a.n_states = (int)h->n_states;
     if (n_new > 0) {
+        if (timing) tk = h->span_begin();
         h->dispatch_group([&](auto g) { finalize_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
+        if (timing) h->span_end(tk, 11);
         ++h->stats.n_launches;
         CK(cudaGetLastError());
     }
@@ -1523,7 +1616,11 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         h->kw = 4 * h->kw4;
         h->n1 = h->n[1];
         h->R = h->L - h->n1;
-        h->G = pow2_group(h->kw4);
+        h->G = std::min(pow2_group(h->kw4), 8);      // measured at L = 4096: 8 lanes per state beat 32 (fewer idle lanes)
+        if (const char *e = getenv("AM_B200_FRONTIER_G")) {     // lanes per state in the frontier / stitching kernels
+            const int g = atoi(e);
+            if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) h->G = std::min(g, h->G);
+        }
         h->skips.assign(h->D + 1, {});
         h->n_tm = 0;
         for (int r = 0; r < arc_rows; ++r) {
@@ -1556,6 +1653,12 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         CK(cudaMallocHost(&h->h_npre, (size_t)(h->D + 3) * 4));
         CK(cudaMallocHost(&h->h_next, (size_t)(h->D + 3) * 4));
         h->next_counts.reserve((size_t)(h->D + 3) * 4);
+        h->level_cursor.reserve((size_t)(h->D + 3) * 4);
+        h->fs_ticket.reserve(64);
+        h->bal_loads.reserve(XCHG_MAX_WORLD * 8);
+        h->bal_cuts.reserve((XCHG_MAX_WORLD + 1) * 4);
+        if (const char *e = getenv("AM_B200_BALANCE")) h->balance = atoi(e) != 0;
+        h->xcursor.reserve(64);
         if (const char *e = getenv("AM_B200_INCREMENTAL")) h->incremental = atoi(e) != 0;
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
         CK(cudaFuncSetAttribute(clip_kernel<3, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
@@ -1776,6 +1879,8 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         h->ev_used = 0;
         h->spans.clear();
         h->stats = am_stats{};
+        h->host_wait_s = 0.0;
+        const auto host_t0 = std::chrono::steady_clock::now();
         cudaEvent_t e_begin = h->ev();
         load_weights(h, W, B, TM, tm_shapes, n_tm);
         {
@@ -1808,6 +1913,10 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         memset(h->h_counters, 0, CNT_NUM * 8);
         if (h->tcap) CK(cudaMemsetAsync(h->table.p, 0xFF, (size_t)h->tcap * 8, st));
         h->table_sharded = h->p2p && h->shard_world > 1;
+        CK(cudaMemsetAsync(h->level_cursor.p, 0, (size_t)(h->D + 3) * 4, st));   // re-armed by the kernels themselves,
+        CK(cudaMemsetAsync(h->fs_ticket.p, 0, 64, st));                          // cleared here in case a march failed
+        CK(cudaMemsetAsync(h->bal_loads.p, 0, XCHG_MAX_WORLD * 8, st));
+        CK(cudaMemsetAsync(h->xcursor.p, 0, 64, st));
         insert_seeds(h, states, pts.data(), n_seeds);
         h->stats.n_seeds = n_seeds;
         h->stats.n_unique_seeds = h->n_states;
@@ -1838,6 +1947,8 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         s.n_over_vertmax = (int64_t)h->h_counters[CNT_OVER_VERTMAX];
         s.n_inconsistent = (int64_t)h->h_counters[CNT_INCONSISTENT];
         s.n_tensors_reloaded = h->stats_layers_reloaded;
+        s.seconds_host_wait = h->host_wait_s;
+        s.seconds_host_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - host_t0).count();
         h->has_march = true;
     } catch (const CudaFail &f) {
         h->err = "am_march: " + f.msg;

@@ -315,6 +315,27 @@ __global__ void scatter_kernel(const int *bucket, int S, int *cursor, int *perm)
     perm[atomicAdd(cursor + bucket[s], 1)] = s;
 }
 
+// classify + scatter in one launch: the host already knows the bucket sizes of the level (histogram produced by
+// the previous level's winner kernel), so the start of every bucket is a launch parameter and a state goes
+// straight to  perm[base[b] + cursor[b]++].  cursor[] must be zero at launch (cleared by the winner kernel).
+struct BucketBase { int base[MAX_LAYERS + 2]; };
+__global__ void classify_scatter_kernel(const int *via_edge, const int *parent, int lb, int S, int prev_lb, int prev_S,
+                                        LayerOffs lo, BucketBase bb, int *bucket, int *cursor, int *perm,
+                                        const uint8_t *owner, int rank)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int e = via_edge[lb + s], p = parent[lb + s];
+    int b = 1;
+    if (owner != nullptr && owner[lb + s] != rank) {
+        b = lo.D + 1;
+    } else if (e >= 0 && p >= prev_lb && p < prev_lb + prev_S) {
+        while (b < lo.D && e >= lo.off[b + 1]) ++b;
+    }
+    bucket[s] = b;
+    perm[bb.base[b] + atomicAdd(cursor + b, 1)] = s;
+}
+
 // rows of hidden layers 2..b of the parent -> own rows; one warp per state
 __global__ void copy_parent_rows_kernel(const int *bucket, const int *parent, int lb, int S, int prev_lb,
                                         const double *prev, double *cur, long long stride, LayerOffs lo, int n1)

@@ -23,6 +23,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace amb {
 namespace cg = cooperative_groups;
@@ -92,6 +93,12 @@ struct LevelArgs {
     // all ranks arrive as one 32-bit mask per parent (bit j = edge slot j discovered a new state)
     int world, rank;                      // world <= 1: single table, winners are read from the table
     const uint32_t *wmask;
+    // fused winner kernel (xchg.cuh winners_scan_kernel): id offset = win_off64[s / FS_TILE] + win_base64[s], low half
+    // = index among the level's children, high half = index among its free children (dealt by `cuts`)
+    const unsigned long long *win_base64, *win_off64;
+    const int *cuts;                      // [world + 1] or nullptr: free child f -> rank r with cuts[r] <= f < cuts[r + 1]
+    int free_below_bit;                   // a child is free when its flipped neuron index is below this (first bit of layer 2)
+    int n_ranks;
 };
 
 __device__ __forceinline__ int key_hash_owner(uint64_t h, int world) { return int(((h >> 32) * (uint64_t)world) >> 32); }
@@ -195,12 +202,19 @@ __global__ void finalize_kernel(const LevelArgs a)
     cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (s >= a.S) return;
-    if (a.nwin[s] == 0) return;
+    if (a.wmask ? (a.wmask[s] == 0u) : (a.nwin[s] == 0)) return;
     const int sid = a.lb + s;
     const long long fo = a.face_off[sid];
     const int k = int(a.face_off[sid + 1] - fo);
     const uint4 *key4 = reinterpret_cast<const uint4 *>(a.keys + (size_t)sid * a.kw);
-    int nid = a.n_states + int(a.win_base[s]);
+    int nid, fidx = 0;
+    if (a.win_base64) {
+        const unsigned long long pr = a.win_base64[s] + a.win_off64[s / FS_TILE];
+        nid = a.n_states + int(uint32_t(pr));
+        fidx = int(pr >> 32);
+    } else {
+        nid = a.n_states + int(a.win_base[s]);
+    }
     const uint32_t wm = a.wmask ? a.wmask[s] : 0u;
     for (int j = 0; j < k; ++j) {
         const int slot = a.cand_slot[(size_t)s * VSLOTS + j];
@@ -224,7 +238,14 @@ __global__ void finalize_kernel(const LevelArgs a)
             a.hsum_w[nid] = hash_flip(a.hsum[sid], a.keys + (size_t)sid * a.kw, e);
             a.parent[nid] = sid;
             a.via_edge[nid] = e;
-            if (a.owner) a.owner[nid] = a.owner[sid];
+            if (a.owner) {
+                int own = a.owner[sid];
+                if (a.cuts != nullptr && e < a.free_below_bit) {      // free child: dealt to level the loads
+                    own = 0;
+                    while (own + 1 < a.n_ranks && fidx >= a.cuts[own + 1]) ++own;
+                }
+                a.owner[nid] = uint8_t(own);
+            }
             const int j2 = (j + 1 == k) ? 0 : j + 1;
             const double *p = a.face_xyz + (size_t)(fo + j) * 3, *q2 = a.face_xyz + (size_t)(fo + j2) * 3;
             const double mx = 0.5 * (p[0] + q2[0]), my = 0.5 * (p[1] + q2[1]), mz = 0.5 * (p[2] + q2[2]);
@@ -242,6 +263,7 @@ __global__ void finalize_kernel(const LevelArgs a)
             if (slot != NO_SLOT) a.table.slots[slot] = (v & 0xFFFFFFFF00000000ull) | uint32_t(nid);
         }
         ++nid;
+        if (a.cuts != nullptr && e < a.free_below_bit) ++fidx;
     }
 }
 

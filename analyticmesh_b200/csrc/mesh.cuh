@@ -69,7 +69,8 @@ __global__ void scan_apply_kernel(const uint32_t *in, int n, const uint32_t *blo
 // ---- face compaction: per-chunk scratch (stride VSLOTS) -> global CSR ----------------------------
 struct CompactArgs {
     const int *cnt;               // [S]
-    const uint32_t *off;          // [S] exclusive scan of cnt
+    const uint32_t *off;          // [S] exclusive scan of cnt (block-local when block_off is given, scan.cuh)
+    const uint32_t *block_off;    // offsets of the FS_TILE blocks, or nullptr
     const int *edges;             // [S][VSLOTS]
     const double *verts;          // [S][VSLOTS][3]
     int S, sid0;
@@ -86,7 +87,7 @@ __global__ void compact_faces_kernel(const CompactArgs a)
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= a.S) return;
-    const long long base = (long long)a.counters[CNT_CORNERS] + a.off[s];
+    const long long base = (long long)a.counters[CNT_CORNERS] + a.off[s] + (a.block_off ? a.block_off[s / FS_TILE] : 0u);
     const int k = a.cnt[s];
     if (lane == 0) {
         a.face_off[a.sid0 + s] = base;

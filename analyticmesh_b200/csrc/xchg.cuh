@@ -163,7 +163,8 @@ struct XchgCompactArgs {
     const unsigned char *own;
     XchgLayout lay;
     const int *cnt_all;
-    const uint32_t *off;          // exclusive scan of cnt_all
+    const uint32_t *off;          // block-local exclusive scan of cnt_all (scan.cuh) ...
+    const uint32_t *block_off;    // ... + offset of the FS_TILE block
     const int2 *where;
     int S, sid0;
     long long *face_off;
@@ -177,7 +178,7 @@ __global__ void xchg_compact_kernel(const XchgCompactArgs a)
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= a.S) return;
-    const long long base = (long long)a.counters[CNT_CORNERS] + a.off[s];
+    const long long base = (long long)a.counters[CNT_CORNERS] + a.off[s] + a.block_off[s / FS_TILE];
     const int k = a.cnt_all[s];
     if (lane == 0) {
         a.face_off[a.sid0 + s] = base;
@@ -209,25 +210,101 @@ __global__ void xchg_push_masks_kernel(const LevelArgs a, XchgPeers p, XchgLayou
     for (int q = 0; q < p.world; ++q) reinterpret_cast<uint32_t *>(p.base[q] + off)[s] = m;
 }
 
-// OR of the masks of all ranks -> winners per parent (+ the bucket histogram of the children this rank will
-// compose, exactly as count_winners_kernel does on a single GPU)
-__global__ void xchg_merge_masks_kernel(const LevelArgs a, const unsigned char *own, XchgLayout lay, int world,
-                                        uint32_t *wmask, LayerOffs lo, int *next_counts, int rank)
+// ---- winners of a level: one launch ------------------------------------------------------------------------
+// Per parent state: the 32-bit winner mask (single GPU / replicated table: read from the visited set; sharded
+// table: OR of the masks pushed by all ranks), the bucket histogram of the children this rank will compose, and
+// the prefix sums that number the children (scan.cuh; two counters at once: winners | free winners << 32).
+//
+// Load balance of the sharded march.  A child normally inherits the owner of its parent, because the plane rows
+// it re-uses live in the parent's level buffer.  A child whose flipped neuron lies in hidden layer 1 re-uses
+// nothing (all layers >= 2 are recomputed, layer 1 is the shared table): it is "free" and may go to any rank.
+// Every rank computes the same per-owner load of the non-free children (integer work units) and the block that
+// finishes last cuts the sequence of free children into `world` runs that level the loads:  free child f goes to
+// the rank r with cuts[r] <= f < cuts[r + 1] (finalize_kernel).  Deterministic, replicated, no communication.
+struct WinArgs {
+    LayerOffs lo;
+    int *next_counts;                  // [D + 3] bucket histogram of the next level's states owned by this rank
+    int rank, world;
+    uint32_t *wmask;                   // [S] out
+    unsigned long long *win_base;      // [S] out: block-local exclusive prefix (winners | free winners << 32)
+    FusedScan64 fs;
+    int *zero_a, n_zero_a, *zero_b;    // small cursors of the next level's kernels, cleared here
+    const unsigned char *own;          // sharded table: this rank's exchange block
+    XchgLayout lay;
+    int balance;                       // deal the free children (sharded modes only)
+    unsigned long long *loads;         // [world] zero at launch, cleared again by the last block
+    int *cuts;                         // [world + 1] out
+    int unit_clip;                     // work of a child = 2 * (recomputed layers) + unit_clip
+};
+
+template <bool SHARDED_TABLE>
+__global__ void __launch_bounds__(FS_THREADS) winners_scan_kernel(const LevelArgs a, const WinArgs w)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.S) return;
-    uint32_t m = 0;
-    for (int r = 0; r < world; ++r) m |= reinterpret_cast<const uint32_t *>(own + lay.mask(r))[s];
-    wmask[s] = m;
-    a.nwin[s] = __popc(m);
-    if (m && a.owner[a.lb + s] == rank) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < w.n_zero_a) w.zero_a[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && w.zero_b) *w.zero_b = 0;
+    const int s0 = blockIdx.x * FS_TILE + threadIdx.x * FS_ITEMS;
+    const int D = w.lo.D;
+    unsigned long long v[FS_ITEMS], e[FS_ITEMS];
+#pragma unroll 1
+    for (int i = 0; i < FS_ITEMS; ++i) {
+        const int s = s0 + i;
+        v[i] = 0;
+        if (s >= a.S) continue;
         const long long fo = a.face_off[a.lb + s];
-        for (uint32_t t = m; t; t &= t - 1) {
-            const int e = a.face_edges[fo + (__ffs(t) - 1)];
-            int b = 1;
-            while (b < lo.D && e >= lo.off[b + 1]) ++b;
-            atomicAdd(next_counts + b, 1);
+        uint32_t m = 0;
+        if (SHARDED_TABLE) {
+            for (int r = 0; r < w.world; ++r) m |= reinterpret_cast<const uint32_t *>(w.own + w.lay.mask(r))[s];
+        } else {
+            const int k = int(a.face_off[a.lb + s + 1] - fo);
+            for (int j = 0; j < k; ++j) {
+                const int slot = a.cand_slot[(size_t)s * VSLOTS + j];
+                if (slot != NO_SLOT && uint32_t(a.table.slots[slot]) == (CAND_TAG | cand_index(s, j))) m |= 1u << j;
+            }
         }
+        w.wmask[s] = m;
+        if (m == 0u) continue;
+        const int own_s = a.owner ? int(a.owner[a.lb + s]) : w.rank;
+        unsigned n_free = 0;
+        unsigned long long units = 0;
+        for (uint32_t t = m; t; t &= t - 1) {
+            const int ed = a.face_edges[fo + (__ffs(t) - 1)];
+            int b = 1;
+            while (b < D && ed >= w.lo.off[b + 1]) ++b;
+            if (w.balance && b == 1) { ++n_free; continue; }
+            units += (unsigned long long)(2 * (D - b) + w.unit_clip);
+            if (own_s == w.rank) atomicAdd(w.next_counts + b, 1);
+        }
+        if (w.balance && units) atomicAdd(w.loads + own_s, units);
+        v[i] = (unsigned long long)__popc(m) | ((unsigned long long)n_free << 32);
+    }
+    unsigned long long total = 0;
+    const bool last = fused_scan_block(v, e, w.fs, &total);
+#pragma unroll
+    for (int i = 0; i < FS_ITEMS; ++i)
+        if (s0 + i < a.S) w.win_base[s0 + i] = e[i];
+    if (last && w.balance && threadIdx.x == 0) {
+        const long long F = (long long)(total >> 32), W = 2 * (D - 1) + w.unit_clip;
+        long long load[XCHG_MAX_WORLD], take[XCHG_MAX_WORLD], sum = 0;
+        for (int r = 0; r < w.world; ++r) {
+            load[r] = (long long)__ldcg(w.loads + r);
+            w.loads[r] = 0;
+            sum += load[r];
+        }
+        const long long target = (sum + F * W + w.world - 1) / w.world;
+        long long rem = F;
+        for (int r = 0; r < w.world; ++r) {
+            long long need = target > load[r] ? (target - load[r]) / W : 0;
+            take[r] = need < rem ? need : rem;
+            rem -= take[r];
+        }
+        int c = 0;
+        for (int r = 0; r < w.world; ++r) {      // what rounding left over: dealt evenly
+            take[r] += rem / w.world + (r < rem % w.world ? 1 : 0);
+            w.cuts[r] = c;
+            c += (int)take[r];
+        }
+        w.cuts[w.world] = c;
+        atomicAdd(w.next_counts + 1, (int)take[w.rank]);
     }
 }
 

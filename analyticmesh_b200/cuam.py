@@ -32,7 +32,9 @@ class AmStats(ctypes.Structure):
         "n_overflow", "n_over_vertmax", "n_inconsistent", "n_vertices", "n_stitch_miss", "max_level_states",
         "n_launches")] + \
         [(n, ctypes.c_double) for n in ("seconds_march", "seconds_compose", "seconds_clip", "seconds_frontier",
-                                        "compose_flops")] + [("n_tensors_reloaded", ctypes.c_int64)]
+                                        "compose_flops")] + [("n_tensors_reloaded", ctypes.c_int64),
+                                                          ("seconds_host_wait", ctypes.c_double),
+                                                          ("seconds_host_total", ctypes.c_double)]
 
 
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",

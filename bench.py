@@ -265,7 +265,11 @@ def main():
         faces += last["n_faces"]
         launches += last["n_launches"]
         engine_s += last["seconds_march"]
-        phases = {k: last[k] for k in ("seconds_compose", "seconds_clip", "seconds_frontier")}
+        phases = {k: last[k] for k in ("seconds_compose", "seconds_clip", "seconds_frontier", "seconds_host_wait",
+                                       "seconds_host_total")}
+        names = {4: "split_gemm", 5: "digits", 6: "xchg_barrier_wait", 7: "xchg_push", 8: "xchg_unpack_scan_csr",
+                 9: "expand_insert", 11: "finalize"}
+        phases["kernel_seconds"] = {v: cuam.kernel_profile(k)["ms_total"] * 1e-3 for k, v in names.items()}
         p = cuam.kernel_profile(prof_kind) if prof_kind is not None else cuam.compose_profile()
         if prof_kind is not None and p["launches"] == 0:      # multi-chain mode records no per-kernel events
             p = cuam.compose_profile()

@@ -60,6 +60,9 @@ typedef struct am_stats {
     double  compose_flops;      /* algorithmic flops executed by the composition kernels */
     int64_t n_tensors_reloaded; /* weight matrices / transforms whose bytes changed since the previous call and were
                                    re-staged on the device (0 when the same network is marched again) */
+    double  seconds_host_wait;  /* host wall time blocked in the per-level synchronisation (GPU-bound when close
+                                   to seconds_host_total, launch-bound when small) */
+    double  seconds_host_total; /* host wall time of am_march */
 } am_stats;
 
 /* replaces cuam.Init (reference backend/src/cuam.cpp:58-95, src/cuam_kernel.cu:128-148).
@@ -171,7 +174,9 @@ int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, 
 int am_compose_profile(const am_handle *h, double *ms_total, int64_t *launches, double *flops);
 
 /* same, per timed span kind: 0 composition launches of a chunk (= am_compose_profile), 1 compose phase,
- * 2 clip, 3 frontier, 4 the tcgen05 split-integer GEMM kernel alone, 5 its digit-extraction kernel.
+ * 2 clip, 3 frontier, 4 the tcgen05 split-integer GEMM kernel alone, 5 its digit-extraction kernel,
+ * 6 exchange barriers of the sharded march (= time waiting for the slowest rank), 7 polygon push, 8 unpack +
+ * scan + CSR, 9 neighbour enumeration + insert, 11 finalize.
  * Kinds 4/5 are recorded per launch with CUDA events on the engine's stream (single-chain mode). */
 int am_kernel_profile(const am_handle *h, int kind, double *ms_total, int64_t *launches, double *flops);
 /* 0/1: FP64 tensor-core (DMMA) tiles, 2: tcgen05 int8 split-integer path; digits of the split (6..8) */
