@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <thread>
@@ -29,6 +30,7 @@
 #include "compose.cuh"
 #include "frontier.cuh"
 #include "mesh.cuh"
+#include "seeds.cuh"
 #include "split.cuh"
 #include "xchg.cuh"
 
@@ -53,6 +55,36 @@ struct CapacityFail : CudaFail {
             throw CudaFail{std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
                            std::to_string(__LINE__) + ")"};                                               \
     } while (0)
+
+// Launch with the programmatic-stream-serialization attribute (common.cuh pdl_enter): the kernel may be scheduled
+// while its predecessor in the stream is still running.  AM_B200_PDL=0 falls back to plain launches.
+// AM_B200_PDL: 0 never, 1 (default) on BFS levels that are small for this rank -- the launch-latency-bound ones;
+// measured on one B200: wide levels run ~5 % slower with the attribute than without -- 2 always.
+int pdl_mode()
+{
+    static const int mode = [] {
+        const char *e = getenv("AM_B200_PDL");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
+}
+thread_local bool g_pdl_now = false;      // set per BFS level by process_level
+
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl_now ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
 
 // ---- virtual-memory backed growth (CUDA VMM through the runtime's driver entry points: no libcuda link)
 struct VmApi {
@@ -392,6 +424,9 @@ struct am_handle {
     const void *b_maps_ptr = nullptr;
     size_t b_maps_ncap = 0;
     static constexpr int MAX_CHAINS = 8;
+    int last_n_chain = 1;
+    long long pdl_below = 4096;                 // states per rank and level below which launches use PDL
+    bool force_perm_order = false;
     int n_chains = 0;   // 0 = automatic: 1 on a single GPU (launches fill the machine), 4 when sharded (measured +1.4 % at 8 GPUs)
     cudaStream_t chain_stream[MAX_CHAINS] = {};
     cudaEvent_t fork_event = nullptr, join_event[MAX_CHAINS] = {};
@@ -409,7 +444,12 @@ struct am_handle {
     XchgLayout xlay{};
     uint32_t xepoch = 0;
     unsigned long long xtimeout_ns = 20000000000ull;
-    DevBuf xcursor, xcnt, xwhere, wmask;
+    DevBuf xcursor, wmask;
+    // native surface-point initialiser (seeds.cuh): row-major FP64 weights, activations, stored seeds
+    std::vector<DevBuf> Wrow, Brow;             // index l = 0..D
+    std::vector<DevBuf> sd_act;                 // index l = 1..D: [P][n_l]
+    DevBuf sd_pts, sd_valid, sd_val, sd_flags, sd_offs, sd_lists, sd_pos, sd_neg, sd_mid, sd_err, sd_tot, sd_keys;
+    long long n_stored_seeds = 0;
     DevBuf bal_loads, bal_cuts;                 // load balance of the sharded march (xchg.cuh winners_scan_kernel)
     bool balance = true;
     DevBuf level_cursor;                        // [D + 3] bucket cursors of classify_scatter_kernel, zero between levels
@@ -420,7 +460,8 @@ struct am_handle {
     DevBuf next_counts;
     bool next_valid = false;
     unsigned long long *h_counters = nullptr;   // pinned
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t win_event = nullptr;
 
     // ---- results ----
     bool has_march = false, has_mesh = false;
@@ -455,7 +496,11 @@ struct am_handle {
         CK(cudaEventRecord(e, stream));
         return e;
     }
-    bool timing_on() const { return ev_used < 60000; }
+    // CUDA events between two kernels serialise them (no programmatic overlap), so the per-phase / per-kernel spans
+    // are recorded on every trace_every-th BFS level only and scaled up (AM_B200_TRACE_EVERY=1: every level)
+    int trace_every = 4, span_scale = 1;
+    bool trace_level = true;
+    bool timing_on() const { return trace_level && ev_used < 60000; }
     size_t span_begin() { ev(); return ev_used - 1; }
     void span_end(size_t a, int kind, double flops = 0.0)
     {
@@ -476,13 +521,22 @@ struct am_handle {
                          &table, &planes, &equ, &f_cnt, &f_off, &f_edges, &f_verts, &cand_slot, &nwin, &wbase, &scan_a,
                          &scan_b, &counters, &xkeys, &xh, &xpt, &xslot, &xstates, &lvl_planes[0], &lvl_planes[1],
                          &bucket, &perm, &bcounts, &owner, &xchg, &cmb_owner, &cmb_flag, &cmb_vid, &cmb_cvid, &cmb_verts,
-                         &digest_acc, &xcursor, &xcnt, &xwhere, &wmask,
-                         &level_cursor, &fs_sums, &fs_off, &fs_sums2, &fs_off2, &fs_ticket, &bal_loads, &bal_cuts};
+                         &digest_acc, &xcursor, &wmask,
+                         &level_cursor, &fs_sums, &fs_off, &fs_sums2, &fs_off2, &fs_ticket, &bal_loads, &bal_cuts,
+                         &sd_pts, &sd_valid, &sd_val, &sd_flags, &sd_offs, &sd_lists, &sd_pos, &sd_neg, &sd_mid, &sd_err, &sd_tot,
+                         &sd_keys};
+        for (auto &b : Wrow) b.release();
+        for (auto &b : Brow) b.release();
+        for (auto &b : sd_act) b.release();
         for (DevBuf *b : all) b->release();
         for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
         ev_pool.clear();
         if (fork_event) cudaEventDestroy(fork_event);
         fork_event = nullptr;
+        if (win_event) cudaEventDestroy(win_event);
+        win_event = nullptr;
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        copy_stream = nullptr;
         for (int c = 0; c < MAX_CHAINS; ++c) {
             if (join_event[c]) cudaEventDestroy(join_event[c]);
             if (chain_stream[c]) cudaStreamDestroy(chain_stream[c]);
@@ -653,11 +707,11 @@ struct am_handle {
         if (t) e0 = span_begin();
         const unsigned sgrid = (unsigned)std::min((Sc + 3) / 4, num_sms * 3);     // persistent warps, 3 CTAs per SM
         if (w.Kpad <= 256)
-            slice_rows_reg_kernel<SD, 2><<<sgrid, 128, 0, cs>>>(sa);
+            launch_k(slice_rows_reg_kernel<SD, 2>, dim3(sgrid), dim3(128), 0, cs, sa);
         else if (w.Kpad <= 512)
-            slice_rows_reg_kernel<SD, 4><<<sgrid, 128, 0, cs>>>(sa);
+            launch_k(slice_rows_reg_kernel<SD, 4>, dim3(sgrid), dim3(128), 0, cs, sa);
         else
-            slice_rows_kernel<SD><<<(unsigned)((Sc + 7) / 8), 256, 0, cs>>>(sa);
+            launch_k(slice_rows_kernel<SD>, dim3((unsigned)((Sc + 7) / 8)), dim3(256), 0, cs, sa);
         ++stats.n_launches;
         if (t) span_end(e0, 5, 0.0);
         SplitArgs g{};
@@ -668,7 +722,7 @@ struct am_handle {
         g.add_identity = accumulate ? 0 : fused_add_identity;
         g.n_tiles = g.m_tiles * mine;
         if (t) e0 = span_begin();
-        split_gemm_kernel<SD><<<(unsigned)std::min(g.n_tiles, num_sms), SP_THREADS, SplitCfg<SD>::SMEM, cs>>>(
+        launch_k(split_gemm_kernel<SD>, dim3((unsigned)std::min(g.n_tiles, num_sms)), dim3(SP_THREADS), SplitCfg<SD>::SMEM, cs, 
             w.map, b_map(w.Kpad), g);
         if (t) span_end(e0, 4, 2.0 * M * (double)K * 4.0 * Sc);
         return true;
@@ -722,13 +776,17 @@ struct am_handle {
     // prm / npre: optional bucket-sorted permutation and, per fc layer h, the number of leading
     // permutation slots whose states need layer h+1 recomputed (incremental mode); null = all states
     // n_equ / equ_idx: states whose level plane is needed (all, or the owned ones in sharded mode)
+    // tail: optional per-chain continuation (the clip launch of the chain's states), run on the chain's stream
+    // right after the chain's level-plane kernel, before the chains join
     void compose_chunk(const uint32_t *keys0, int S_all, double iso, double *base, const int *prm, const int *npre,
-                       int n_equ, const int *equ_idx)
+                       int n_equ, const int *equ_idx,
+                       const std::function<void(int, int, cudaStream_t)> *tail = nullptr)
     {
         // The layer launches of one chunk form a dependency chain (layer h+1 reads layer h of the same
         // states).  The state tiles are dealt round-robin to n_chain independent chains on separate
         // streams, so the tail of one chain's launch is filled by the others' CTAs.
-        const int n_chain = (D >= 3) ? (n_chains > 0 ? n_chains : ((shard_world > 1 && gemm_variant != 2) ? 4 : 1)) : 1;
+        const int n_chain = planned_chains();
+        last_n_chain = n_chain;
         if (gemm_variant == 2) ensure_split_scratch((size_t)S_all);
         const bool timed = timing_on();
         size_t span0 = 0;
@@ -795,6 +853,52 @@ struct am_handle {
                 }
             }
         }
+        auto launch_equ = [&](int c, int nc, cudaStream_t cs) {
+            EquArgs e{};
+            e.w = wout.as<double>();
+            e.bias = bout;
+            e.iso = iso;
+            e.in = layer_rows(base, D, &e.in_stride);
+            const int Sc = n_equ;
+            if (Sc <= 0) return;
+            e.idx = equ_idx;
+            e.keys = keys0; e.kw = kw; e.bit0 = off[D]; e.K = n[D]; e.S = Sc;
+            e.equ = equ.as<double>();
+            e.bucket = nullptr;
+            e.tile_stride = nc; e.tile_offset = c; e.tile = chain_tile();
+            if (lazy_prev != nullptr && D >= 2) {
+                e.bucket = bucket.as<int>(); e.parent = parent.as<int>();
+                e.lb = (int)lazy_lb; e.prev_lb = (int)lazy_prev_lb; e.D = D;
+                e.alt_in = lazy_prev + 4LL * (off[D] - n1);
+            }
+            e.n_skips = 0;
+            for (const Skip &sk : skips[D]) {
+                if (e.n_skips == EQU_MAX_SKIPS) throw CudaFail{"more than 4 skips into the output layer"};
+                EquSkip &q = e.skips[e.n_skips++];
+                const bool identity = (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0);
+                q.T = identity ? nullptr : TM[sk.tm].as<double>();
+                q.src = nullptr; q.src_stride = 0; q.src_bit0 = 0; q.src_n = 0;
+                if (sk.src == 0) {
+                    q.kind = identity ? 1 : 2;
+                } else {
+                    q.kind = identity ? 3 : 4;
+                    q.src = layer_rows(base, sk.src, &q.src_stride);
+                    q.src_bit0 = off[sk.src];
+                    q.src_n = n[sk.src];
+                }
+            }
+            const int mine = chain_slots(Sc, c, nc);
+            if (mine <= 0) return;
+            launch_k(equ_kernel, dim3((mine * 4 + 127) / 128), dim3(128), 0, cs, e);
+            ++stats.n_launches;
+            CK(cudaGetLastError());
+        };
+        const bool chained_tail = (tail != nullptr) && n_chain > 1;
+        if (chained_tail)
+            for (int c = 0; c < n_chain; ++c) {
+                launch_equ(c, n_chain, chain_stream[c]);
+                (*tail)(c, n_chain, chain_stream[c]);
+            }
         if (n_chain > 1) {
             for (int c = 0; c < n_chain; ++c) {
                 CK(cudaEventRecord(join_event[c], chain_stream[c]));
@@ -802,41 +906,23 @@ struct am_handle {
             }
         }
         if (timed) span_end(span0, 0, pending_gemm_flops);
-        EquArgs e{};
-        e.w = wout.as<double>();
-        e.bias = bout;
-        e.iso = iso;
-        e.in = layer_rows(base, D, &e.in_stride);
-        const int Sc = n_equ;
-        if (Sc <= 0) return;
-        e.idx = equ_idx;
-        e.keys = keys0; e.kw = kw; e.bit0 = off[D]; e.K = n[D]; e.S = Sc;
-        e.equ = equ.as<double>();
-        e.bucket = nullptr;
-        if (lazy_prev != nullptr && D >= 2) {
-            e.bucket = bucket.as<int>(); e.parent = parent.as<int>();
-            e.lb = (int)lazy_lb; e.prev_lb = (int)lazy_prev_lb; e.D = D;
-            e.alt_in = lazy_prev + 4LL * (off[D] - n1);
+        if (!chained_tail) {
+            launch_equ(0, 1, stream);
+            if (tail != nullptr) (*tail)(0, 1, stream);
         }
-        e.n_skips = 0;
-        for (const Skip &sk : skips[D]) {
-            if (e.n_skips == EQU_MAX_SKIPS) throw CudaFail{"more than 4 skips into the output layer"};
-            EquSkip &q = e.skips[e.n_skips++];
-            const bool identity = (tm_h[sk.tm] == 0 && tm_w[sk.tm] == 0);
-            q.T = identity ? nullptr : TM[sk.tm].as<double>();
-            q.src = nullptr; q.src_stride = 0; q.src_bit0 = 0; q.src_n = 0;
-            if (sk.src == 0) {
-                q.kind = identity ? 1 : 2;
-            } else {
-                q.kind = identity ? 3 : 4;
-                q.src = layer_rows(base, sk.src, &q.src_stride);
-                q.src_bit0 = off[sk.src];
-                q.src_n = n[sk.src];
-            }
-        }
-        equ_kernel<<<(Sc * 4 + 127) / 128, 128, 0, stream>>>(e);
-        ++stats.n_launches;
-        CK(cudaGetLastError());
+    }
+
+    // slots of a list of n handled by chain c of nc: whole tiles of SP_BS slots dealt round-robin (the same deal as
+    // the composition launches, so a chain only depends on its own kernels)
+    int planned_chains() const { return (D >= 3) ? (n_chains > 0 ? n_chains : (shard_world > 1 ? 4 : 1)) : 1; }
+    int chain_tile() const { return gemm_variant == 2 ? SP_BS : (gemm_variant == 1 ? GemmWide::BS : GemmDefault::BS); }
+    int chain_slots(int n, int c, int nc) const
+    {
+        if (nc <= 1) return n;
+        const int ct = chain_tile();
+        const int tiles = (n + ct - 1) / ct;
+        const int mine = (tiles - c + nc - 1) / nc;
+        return mine > 0 ? mine * ct : 0;
     }
 
     size_t chunk_states() const
@@ -1005,6 +1091,8 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
                 p1[4 * r + 3] = b0[r];
             }
             upload(h->P1, p1.data(), p1.size() * 8, h->stream);
+            upload(h->Wrow[0], w0.data(), w0.size() * 8, h->stream);
+            upload(h->Brow[0], b0.data(), b0.size() * 8, h->stream);
             CK(cudaStreamSynchronize(h->stream));
             ++h->stats_layers_reloaded;
         }
@@ -1017,11 +1105,13 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
         if (cb) {
             auto b = cached_real(h, 2 * l + 1, (size_t)M);
             upload(h->bias[l], b.data(), b.size() * 8, h->stream);
+            upload(h->Brow[l], b.data(), b.size() * 8, h->stream);
             CK(cudaStreamSynchronize(h->stream));
         }
         if (!cw) continue;
         ++h->stats_layers_reloaded;
         auto w = cached_real(h, 2 * l, (size_t)M * K);
+        upload(h->Wrow[l], w.data(), w.size() * 8, h->stream);
         if (h->gemm_variant != 2) {      // k-major FP64 copy: the DMMA path only
             std::vector<double> wt((size_t)Kp * Mp, 0.0);
             for (int m = 0; m < M; ++m)
@@ -1037,9 +1127,15 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
         if (cw) {
             auto w = cached_real(h, 2 * D, (size_t)h->n[D]);
             upload(h->wout, w.data(), w.size() * 8, h->stream);
+            upload(h->Wrow[D], w.data(), w.size() * 8, h->stream);
             CK(cudaStreamSynchronize(h->stream));
         }
-        if (cw || cb) h->bout = cached_real(h, 2 * D + 1, 1)[0];
+        if (cw || cb) {
+            auto b = cached_real(h, 2 * D + 1, 1);
+            h->bout = b[0];
+            upload(h->Brow[D], b.data(), 8, h->stream);
+            CK(cudaStreamSynchronize(h->stream));
+        }
     }
     h->TM.resize(n_tm); h->TMt.resize(n_tm);
     h->splitTM.resize(n_tm);
@@ -1086,24 +1182,31 @@ int load_weights(am_handle *h, const void *const *W, const void *const *B, const
     return AM_OK;
 }
 
+// states == nullptr: the seeds found by am_seed_dichotomy (packed keys + points, already on the device)
 void insert_seeds(am_handle *h, const uint8_t *states, const double *points, long long N)
 {
     cudaStream_t st = h->stream;
-    h->xstates.reserve((size_t)N * h->L, 0, false);
-    if (classify(states) == PK_DEVICE)
-        CK(cudaMemcpyAsync(h->xstates.p, states, (size_t)N * h->L, cudaMemcpyDeviceToDevice, st));
-    else
-        CK(cudaMemcpyAsync(h->xstates.p, states, (size_t)N * h->L, cudaMemcpyHostToDevice, st));
     h->xkeys.reserve((size_t)N * h->kw * 4, 0, false);
     h->xh.reserve((size_t)N * 8, 0, false);
     h->xslot.reserve((size_t)N * 4, 0, false);
-    upload(h->xpt, points, (size_t)N * 24, st);
     h->nwin.reserve((size_t)N * 4, 0, false);
     h->wbase.reserve((size_t)N * 4, 0, false);
-    const long long tot = N * h->kw;
-    pack_states_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->xstates.as<uint8_t>(), (int)N, h->L, h->kw,
-                                                                     h->xkeys.as<uint32_t>());
-    ++h->stats.n_launches;
+    if (states == nullptr) {
+        h->xpt.reserve((size_t)N * 24, 0, false);
+        CK(cudaMemcpyAsync(h->xkeys.p, h->sd_keys.p, (size_t)N * h->kw * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(h->xpt.p, h->sd_mid.p, (size_t)N * 24, cudaMemcpyDeviceToDevice, st));
+    } else {
+        h->xstates.reserve((size_t)N * h->L, 0, false);
+        if (classify(states) == PK_DEVICE)
+            CK(cudaMemcpyAsync(h->xstates.p, states, (size_t)N * h->L, cudaMemcpyDeviceToDevice, st));
+        else
+            CK(cudaMemcpyAsync(h->xstates.p, states, (size_t)N * h->L, cudaMemcpyHostToDevice, st));
+        upload(h->xpt, points, (size_t)N * 24, st);
+        const long long tot = N * h->kw;
+        pack_states_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->xstates.as<uint8_t>(), (int)N, h->L, h->kw,
+                                                                         h->xkeys.as<uint32_t>());
+        ++h->stats.n_launches;
+    }
     hash_keys_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->xkeys.as<uint32_t>(), (int)N, h->kw,
                                                                  h->xh.as<unsigned long long>());
     ++h->stats.n_launches;
@@ -1150,10 +1253,13 @@ Scratch scratch_of(am_handle *h, size_t S)
 }
 
 // clip the states idx[0..n) (or all Sc states when idx == nullptr) of the range starting at sid0
-void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, int flip, const int *idx, Scratch sc)
+void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, int flip, const int *idx, Scratch sc,
+              int chain = 0, int n_chain = 1, cudaStream_t cs = nullptr)
 {
     if (n <= 0) return;
-    cudaStream_t st = h->stream;
+    cudaStream_t st = cs ? cs : h->stream;
+    const int mine = h->chain_slots(n, chain, n_chain);
+    if (mine <= 0) return;
     ClipArgs ca{};
     ca.keys = h->keys.as<uint32_t>() + (size_t)sid0 * h->kw; ca.kw = h->kw;
     ca.P1 = h->P1.as<double>(); ca.n1 = h->n1;
@@ -1171,10 +1277,11 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     for (int l = 1; l <= h->D + 1; ++l) ca.lo.off[l] = h->off[l];
     ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
     ca.counters = h->counters.as<unsigned long long>();
-    const unsigned cgrid = (unsigned)((n + CLIP_WARPS - 1) / CLIP_WARPS);
+    ca.tile_stride = n_chain; ca.tile_offset = chain; ca.tile = h->chain_tile();
+    const unsigned cgrid = (unsigned)((mine + CLIP_WARPS - 1) / CLIP_WARPS);
     switch (h->clip_minb) {   // AM_B200_CLIP_MINB: 2 = two CTAs/SM, no spills (default); 3 = three CTAs/SM
-        case 3: clip_kernel<3, 2, 3><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 3), st>>>(ca); break;
-        default: clip_kernel<2, 2, 3><<<cgrid, CLIP_WARPS * 32, clip_ring_bytes(2, 3), st>>>(ca); break;
+        case 3: launch_k(clip_kernel<3, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
+        default: launch_k(clip_kernel<2, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
     }
     ++h->stats.n_launches;
     CK(cudaGetLastError());
@@ -1195,7 +1302,7 @@ void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc, bool fused = 
         // one launch scans the polygon sizes (block-local prefix + block offsets), one copies the polygons; the
         // running corner total is advanced by the level's winner kernel (process_level)
         FusedScan fs = h->fused_scan(Sc, 0, cnt + CNT_CHUNK_CORNERS);
-        scan_local_kernel<<<(Sc + FS_TILE - 1) / FS_TILE, FS_THREADS, 0, st>>>(reinterpret_cast<uint32_t *>(sc.cnt), Sc,
+        launch_k(scan_local_kernel, dim3((Sc + FS_TILE - 1) / FS_TILE), dim3(FS_THREADS), 0, st, reinterpret_cast<uint32_t *>(sc.cnt), Sc,
                                                                              h->f_off.as<uint32_t>(), fs);
         ++h->stats.n_launches;
         CompactArgs co{};
@@ -1205,7 +1312,7 @@ void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc, bool fused = 
         co.S = Sc; co.sid0 = (int)sid0;
         co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
         co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
-        compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
+        launch_k(compact_faces_kernel, dim3((Sc + 7) / 8), dim3(256), 0, st, co);
         ++h->stats.n_launches;
         CK(cudaGetLastError());
         return;
@@ -1231,7 +1338,7 @@ void store_faces(am_handle *h, long long sid0, int Sc, Scratch sc, bool fused = 
     co.S = Sc; co.sid0 = (int)sid0;
     co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
     co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
-    compact_faces_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
+    launch_k(compact_faces_kernel, dim3((Sc + 7) / 8), dim3(256), 0, st, co);
     ++h->stats.n_launches;
     if (sharded && n_lvl > 0) {
         h->allreduce_i32(h->face_edges.as<int>() + base, n_lvl);
@@ -1251,7 +1358,7 @@ void xchg_barrier(am_handle *h)
     const bool t = h->timing_on();
     size_t e0 = 0;
     if (t) e0 = h->span_begin();
-    xchg_barrier_kernel<<<1, 32, 0, h->stream>>>(h->xpeers, h->xepoch, h->xtimeout_ns, h->counters.as<unsigned long long>());
+    launch_k(xchg_barrier_kernel, dim3(1), dim3(32), 0, h->stream, h->xpeers, h->xepoch, h->xtimeout_ns, h->counters.as<unsigned long long>());
     if (t) h->span_end(e0, 6);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
@@ -1261,39 +1368,35 @@ void store_faces_p2p(am_handle *h, long long sid0, int Sc, Scratch sc, const int
 {
     cudaStream_t st = h->stream;
     unsigned long long *cnt = h->counters.as<unsigned long long>();
-    if (n_mine > h->xlay.cap_states)
-        throw CapacityFail{"sharded march: " + std::to_string(n_mine) + " states of one rank in one BFS level exceed the "
-                           "exchange region (raise AM_B200_XCHG_MIB)"};
-    h->xcursor.reserve(64);
-    h->xcnt.reserve((size_t)Sc * 4, 0, false);
-    h->xwhere.reserve((size_t)Sc * 8, 0, false);
+    if (Sc > h->xlay.mask_cap)
+        throw CapacityFail{"sharded march: a BFS level of " + std::to_string(Sc) + " states exceeds the exchange block "
+                           "(raise AM_B200_XCHG_LEVEL_STATES)"};
     h->f_off.reserve((size_t)Sc * 4, 0, false);
-    XchgPackArgs pa{};      // the cursor is zero: cleared by the previous level's winner kernel
-    pa.idx = idx; pa.n = n_mine; pa.cnt = sc.cnt; pa.edges = sc.edges; pa.verts = sc.verts;
-    pa.cursor = h->xcursor.as<int>(); pa.p = h->xpeers; pa.lay = h->xlay; pa.counters = cnt;
     const bool tm = h->timing_on();
     size_t e0 = 0;
-    if (tm) e0 = h->span_begin();
-    xchg_pack_kernel<<<(unsigned)std::max(1, (n_mine + 7) / 8), 256, 0, st>>>(pa);
-    if (tm) h->span_end(e0, 7);
-    ++h->stats.n_launches;
+    if (n_mine > 0) {
+        XchgPackArgs pa{};      // the cursor is zero: cleared by the previous level's winner kernel
+        pa.idx = idx; pa.n = n_mine; pa.cnt = sc.cnt; pa.edges = sc.edges; pa.verts = sc.verts;
+        pa.cursor = h->xcursor.as<int>(); pa.p = h->xpeers; pa.lay = h->xlay; pa.counters = cnt;
+        if (tm) e0 = h->span_begin();
+        launch_k(xchg_pack_kernel, dim3((unsigned)((n_mine + 7) / 8)), dim3(256), 0, st, pa);
+        if (tm) h->span_end(e0, 7);
+        ++h->stats.n_launches;
+    }
     xchg_barrier(h);
     if (tm) e0 = h->span_begin();
     const unsigned char *own = h->xpeers.base[h->shard_rank];
-    dim3 ug((unsigned)std::max(1, std::min((Sc + 255) / 256, 64)), (unsigned)h->shard_world);
-    xchg_unpack_kernel<<<ug, 256, 0, st>>>(own, h->xlay, Sc, h->xcnt.as<int>(), h->xwhere.as<int2>(), cnt);
-    ++h->stats.n_launches;
-    CK(cudaGetLastError());
+    const uint32_t *cnt_all = reinterpret_cast<const uint32_t *>(own + h->xlay.cnt_base);
     FusedScan fs = h->fused_scan(Sc, 0, cnt + CNT_CHUNK_CORNERS);
-    scan_local_kernel<<<(Sc + FS_TILE - 1) / FS_TILE, FS_THREADS, 0, st>>>(h->xcnt.as<uint32_t>(), Sc, h->f_off.as<uint32_t>(), fs);
+    launch_k(scan_local_kernel, dim3((Sc + FS_TILE - 1) / FS_TILE), dim3(FS_THREADS), 0, st, cnt_all, Sc, h->f_off.as<uint32_t>(), fs);
     ++h->stats.n_launches;
     XchgCompactArgs co{};
-    co.own = own; co.lay = h->xlay; co.cnt_all = h->xcnt.as<int>(); co.off = h->f_off.as<uint32_t>();
+    co.own = own; co.lay = h->xlay; co.cnt_all = reinterpret_cast<const int *>(cnt_all); co.off = h->f_off.as<uint32_t>();
     co.block_off = fs.block_off;
-    co.where = h->xwhere.as<int2>(); co.S = Sc; co.sid0 = (int)sid0;
+    co.where = reinterpret_cast<const int2 *>(own + h->xlay.where_base); co.S = Sc; co.sid0 = (int)sid0;
     co.face_off = h->face_off.as<long long>(); co.face_edges = h->face_edges.as<int>();
     co.face_xyz = h->face_xyz.as<double>(); co.counters = cnt;
-    xchg_compact_kernel<<<(Sc + 7) / 8, 256, 0, st>>>(co);
+    launch_k(xchg_compact_kernel, dim3((Sc + 7) / 8), dim3(256), 0, st, co);
     if (tm) h->span_end(e0, 8);
     ++h->stats.n_launches;
     CK(cudaGetLastError());
@@ -1303,6 +1406,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
 {
     cudaStream_t st = h->stream;
     const long long S = le - lb;
+    g_pdl_now = pdl_mode() == 2 || (pdl_mode() == 1 && S / std::max(1, h->shard_world) < h->pdl_below);
     // candidate index = (state within the level << 5) | edge slot under the CAND_TAG bit (frontier.cuh cand_index)
     if (S >= (1LL << 26)) throw CapacityFail{"a BFS level of " + std::to_string(S) + " states exceeds the 2^26 candidate index"};
     unsigned long long *cnt = h->counters.as<unsigned long long>();
@@ -1360,7 +1464,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         if (have) {      // bucket sizes known: classify + scatter in one launch, bucket starts as launch parameters
             BucketBase bb{};
             for (int b = 1; b <= D + 1; ++b) bb.base[b] = npre[b - 1];
-            classify_scatter_kernel<<<sb, 256, 0, st>>>(h->via.as<int>(), h->parent.as<int>(), (int)lb, (int)S,
+            launch_k(classify_scatter_kernel, dim3(sb), dim3(256), 0, st, h->via.as<int>(), h->parent.as<int>(), (int)lb, (int)S,
                                                         h->prev_resident ? (int)h->prev_lb : 0,
                                                         h->prev_resident ? (int)h->prev_S : 0, lo, bb, h->bucket.as<int>(),
                                                         h->level_cursor.as<int>(), h->perm.as<int>(),
@@ -1399,11 +1503,24 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         }
         const int n_mine = npre[D];                       // states this rank composes and clips
         h->shard_owned_states += n_mine;
-        h->compose_chunk(keys0, (int)S, iso, base, h->perm.as<int>(), npre.data(), sharded ? n_mine : (int)S,
-                         sharded ? h->perm.as<int>() : nullptr);
-        if (timing) h->span_end(t0, 1);
-        if (timing) t0 = h->span_begin();
-        run_clip(h, lb, sharded ? n_mine : (int)S, base, flip, sharded ? h->perm.as<int>() : nullptr, sc);
+        // every chain clips its own states right after composing them (perm covers all S states when not sharded)
+        const int n_clip = sharded ? n_mine : (int)S;
+        // a single chain on one GPU walks the states in id order (siblings are neighbours: better DRAM / TLB locality
+        // than the bucket-sorted order); chains and the sharded march go through the permutation
+        const bool in_order = !sharded && h->planned_chains() == 1 && !h->force_perm_order;
+        const int *order = in_order ? nullptr : h->perm.as<int>();
+        const std::function<void(int, int, cudaStream_t)> tail = [&](int c, int nc, cudaStream_t cs) {
+            if (nc == 1) {
+                if (timing) h->span_end(t0, 1);
+                if (timing) t0 = h->span_begin();
+            }
+            run_clip(h, lb, n_clip, base, flip, order, sc, c, nc, cs);
+        };
+        h->compose_chunk(keys0, (int)S, iso, base, h->perm.as<int>(), npre.data(), n_clip, order, &tail);
+        if (h->last_n_chain > 1 && timing) {     // chained: the compose span covers the chains' clip launches too
+            h->span_end(t0, 1);
+            t0 = h->span_begin();
+        }
         if (sharded && h->p2p) store_faces_p2p(h, lb, (int)S, sc, h->perm.as<int>(), n_mine);   // NVLink peer pushes
         else store_faces(h, lb, (int)S, sc, /*fused=*/!sharded);   // sharded (NCCL scheme): + the level's collectives
         h->lazy_prev = nullptr;
@@ -1445,6 +1562,9 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     const bool timing = h->timing_on();
     if (timing) t0 = h->span_begin();
     h->ensure_table((size_t)h->n_states + (size_t)S * VSLOTS);
+    // room for the children before their number is known (a level usually discovers about as many states as it
+    // holds); finalize_kernel is guarded and re-run in the rare case that this was not enough
+    h->ensure_states((size_t)h->n_states + (size_t)std::min<long long>(S * VSLOTS, 2 * S + 65536));
     h->cand_slot.reserve((size_t)S * VSLOTS * 4, 0, false);
     h->nwin.reserve((size_t)S * 4, 0, false);
     h->wbase.reserve((size_t)S * 4, 0, false);
@@ -1466,7 +1586,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         throw CapacityFail{"sharded march: a BFS level of " + std::to_string(S) + " states exceeds the winner-mask region"};
     size_t tk = 0;
     if (timing) tk = h->span_begin();
-    h->dispatch_group([&](auto g) { expand_insert_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
+    h->dispatch_group([&](auto g) { launch_k(expand_insert_kernel<decltype(g)::value>, dim3(gb), dim3(256), 0, st, a); });
     if (timing) h->span_end(tk, 9);
     ++h->stats.n_launches;
     {
@@ -1496,12 +1616,12 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         w.unit_clip = 3;
         const unsigned wb = (unsigned)((S + FS_TILE - 1) / FS_TILE);
         if (p2p) {   // winners of the candidates whose hash this rank owns -> every rank; OR after the barrier
-            xchg_push_masks_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(a, h->xpeers, h->xlay);
+            launch_k(xchg_push_masks_kernel, dim3((unsigned)((S + 255) / 256)), dim3(256), 0, st, a, h->xpeers, h->xlay);
             ++h->stats.n_launches;
             xchg_barrier(h);
-            winners_scan_kernel<true><<<wb, FS_THREADS, 0, st>>>(a, w);
+            launch_k(winners_scan_kernel<true>, dim3(wb), dim3(FS_THREADS), 0, st, a, w);
         } else {
-            winners_scan_kernel<false><<<wb, FS_THREADS, 0, st>>>(a, w);
+            launch_k(winners_scan_kernel<false>, dim3(wb), dim3(FS_THREADS), 0, st, a, w);
         }
         a.wmask = w.wmask;
         a.win_base64 = w.win_base; a.win_off64 = w.fs.block_off;
@@ -1511,10 +1631,32 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         ++h->stats.n_launches;
         CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(h->h_next, h->next_counts.p, (size_t)(h->D + 3) * 4, cudaMemcpyDeviceToHost, st));
+    // The winners' appends are launched at once (the arenas were grown speculatively above); the level's counters
+    // travel to the host on a second stream meanwhile, so the host learns n_new -- and enqueues the next level --
+    // while finalize_kernel is still running: no idle gap around the level's one host synchronisation.
+    CK(cudaEventRecord(h->win_event, st));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->win_event, 0));
+    CK(cudaMemcpyAsync(h->h_next, h->next_counts.p, (size_t)(h->D + 3) * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaMemcpyAsync(h->h_counters, h->counters.p, CNT_NUM * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+    auto launch_finalize = [&]() {
+        a.keys = h->keys.as<uint32_t>(); a.hsum = h->hsum.as<unsigned long long>();
+        a.face_off = h->face_off.as<long long>();
+        a.keys_w = h->keys.as<uint32_t>(); a.hsum_w = h->hsum.as<unsigned long long>();
+        a.parent = h->parent.as<int>(); a.via_edge = h->via.as<int>(); a.seedpt = h->seedpt.as<double>();
+        a.owner = h->shard_world > 1 ? h->owner.as<uint8_t>() : nullptr;
+        a.n_states = (int)h->n_states;
+        a.cap_states = (int)std::min<size_t>(h->cap_states, (size_t)0x7FFFFFFF);
+        if (timing) tk = h->span_begin();
+        h->dispatch_group([&](auto g) { launch_k(finalize_kernel<decltype(g)::value>, dim3(gb), dim3(256), 0, st, a); });
+        if (timing) h->span_end(tk, 11);
+        ++h->stats.n_launches;
+        CK(cudaGetLastError());
+    };
+    const size_t cap_at_launch = h->cap_states;
+    launch_finalize();
     {
         const auto w0 = std::chrono::steady_clock::now();
-        h->read_counters();                               // the one host sync of the level
+        CK(cudaStreamSynchronize(h->copy_stream));        // the one host sync of the level
         h->host_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
     }
     h->next_valid = true;
@@ -1526,19 +1668,9 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
     }
     const long long n_new = (long long)h->h_counters[CNT_NEW];
     if (h->n_states + n_new >= (1LL << 31) - 1) throw CapacityFail{"more than 2^31 states"};
-    h->ensure_states((size_t)(h->n_states + n_new));
-    a.keys = h->keys.as<uint32_t>(); a.hsum = h->hsum.as<unsigned long long>();   // arenas may have moved
-    a.face_off = h->face_off.as<long long>();
-    a.keys_w = h->keys.as<uint32_t>(); a.hsum_w = h->hsum.as<unsigned long long>();
-    a.parent = h->parent.as<int>(); a.via_edge = h->via.as<int>(); a.seedpt = h->seedpt.as<double>();
-    a.owner = h->shard_world > 1 ? h->owner.as<uint8_t>() : nullptr;
-    a.n_states = (int)h->n_states;
-    if (n_new > 0) {
-        if (timing) tk = h->span_begin();
-        h->dispatch_group([&](auto g) { finalize_kernel<decltype(g)::value><<<gb, 256, 0, st>>>(a); });
-        if (timing) h->span_end(tk, 11);
-        ++h->stats.n_launches;
-        CK(cudaGetLastError());
+    if ((size_t)(h->n_states + n_new) > cap_at_launch) {   // more children than reserved: the guarded kernel skipped them
+        h->ensure_states((size_t)(h->n_states + n_new));
+        launch_finalize();                                 // idempotent
     }
     if (timing) h->span_end(t0, 3);
     h->n_states += n_new;
@@ -1570,11 +1702,13 @@ void resolve_spans(am_handle *h)
     for (const auto &s : h->spans) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev_pool[s.a], h->ev_pool[s.b]) != cudaSuccess) { cudaGetLastError(); continue; }
+        const double sc = (double)h->span_scale;       // sampled levels -> estimate for the whole march
+        ms *= (float)sc;
         ms_k[s.kind] += ms;
         h->kind_ms[s.kind] += ms;
-        h->kind_flops[s.kind] += s.flops;
-        h->kind_launches[s.kind]++;
-        if (s.kind == 0) { h->gemm_flops += s.flops; h->gemm_launches++; }
+        h->kind_flops[s.kind] += s.flops * sc;
+        h->kind_launches[s.kind] += h->span_scale;
+        if (s.kind == 0) { h->gemm_flops += s.flops * sc; h->gemm_launches += h->span_scale; }
     }
     h->gemm_ms = ms_k[0];
     h->stats.seconds_compose = ms_k[1] * 1e-3;
@@ -1639,8 +1773,11 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
                           &h->planes, &h->table, &h->cmb_owner, &h->cmb_flag, &h->cmb_vid, &h->cmb_cvid, &h->cmb_verts})
             b->vm = true;
         h->Wt.resize(h->D + 1); h->bias.resize(h->D + 1);
+        h->Wrow.resize(h->D + 1); h->Brow.resize(h->D + 1); h->sd_act.resize(h->D + 1);
         h->Mpad.assign(h->D + 1, 0); h->Kpad.assign(h->D + 1, 0);
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->win_event, cudaEventDisableTiming));
         if (const char *e = getenv("AM_B200_CHAINS")) h->n_chains = std::max(0, std::min(am_handle::MAX_CHAINS, atoi(e)));
         CK(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
         for (int c = 0; c < am_handle::MAX_CHAINS; ++c) {
@@ -1658,6 +1795,9 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         h->bal_loads.reserve(XCHG_MAX_WORLD * 8);
         h->bal_cuts.reserve((XCHG_MAX_WORLD + 1) * 4);
         if (const char *e = getenv("AM_B200_BALANCE")) h->balance = atoi(e) != 0;
+        if (const char *e = getenv("AM_B200_PERM_ORDER")) h->force_perm_order = atoi(e) != 0;
+        if (const char *e = getenv("AM_B200_TRACE_EVERY")) h->trace_every = std::max(1, atoi(e));
+        if (const char *e = getenv("AM_B200_PDL_BELOW")) h->pdl_below = atoll(e);
         h->xcursor.reserve(64);
         if (const char *e = getenv("AM_B200_INCREMENTAL")) h->incremental = atoi(e) != 0;
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
@@ -1784,6 +1924,194 @@ int am_set_shard_nccl(am_handle *h, int rank, int world, const void *unique_id12
     return AM_OK;
 }
 
+namespace {
+
+// f(points) for P points [P][3] on the device -> h->sd_val[P]; optionally the packed activation keys
+void seed_forward(am_handle *h, const double *pts, int P, uint32_t *keys)
+{
+    cudaStream_t st = h->stream;
+    const int D = h->D;
+    auto gemm = [&](const double *in, int ldi, const double *W, const double *b, double *out, int ldo, int M, int K, int acc) {
+        dim3 grid((unsigned)((M + SG_T - 1) / SG_T), (unsigned)((P + SG_T - 1) / SG_T));
+        seed_gemm_kernel<<<grid, 256, 0, st>>>(in, ldi, W, b, out, ldo, P, M, K, acc);
+        ++h->stats.n_launches;
+    };
+    auto skips_into = [&](int hfc, double *out, int ldo, int M) {      // fc layer hfc: hidden hfc -> hidden hfc + 1 / output
+        for (const Skip &sk : h->skips[hfc]) {
+            const bool identity = (h->tm_h[sk.tm] == 0 && h->tm_w[sk.tm] == 0);
+            const double *src = (sk.src == 0) ? pts : h->sd_act[sk.src].as<double>();
+            const int lds = (sk.src == 0) ? 3 : h->n[sk.src];
+            if (identity) {
+                const int m = std::min(M, lds);
+                seed_add_kernel<<<(unsigned)(((long long)P * m + 255) / 256), 256, 0, st>>>(out, ldo, src, lds, P, m);
+                ++h->stats.n_launches;
+            } else {
+                gemm(src, lds, h->TM[sk.tm].as<double>(), nullptr, out, ldo, M, lds, 1);
+            }
+        }
+    };
+    if (keys) CK(cudaMemsetAsync(keys, 0, (size_t)P * h->kw * 4, st));
+    for (int l = 1; l <= D; ++l) h->sd_act[l].reserve((size_t)P * h->n[l] * 8, 0, false);
+    gemm(pts, 3, h->Wrow[0].as<double>(), h->Brow[0].as<double>(), h->sd_act[1].as<double>(), h->n[1], h->n[1], 3, 0);
+    for (int l = 1; l <= D; ++l) {
+        if (l >= 2) skips_into(l - 1, h->sd_act[l].as<double>(), h->n[l], h->n[l]);
+        const int words = (h->n[l] + 31) / 32;
+        seed_relu_bits_kernel<<<(unsigned)(((long long)P * words + 255) / 256), 256, 0, st>>>(
+            h->sd_act[l].as<double>(), h->n[l], P, h->n[l], h->off[l], keys, h->kw);
+        ++h->stats.n_launches;
+        if (l < D)
+            gemm(h->sd_act[l].as<double>(), h->n[l], h->Wrow[l].as<double>(), h->Brow[l].as<double>(),
+                 h->sd_act[l + 1].as<double>(), h->n[l + 1], h->n[l + 1], h->n[l], 0);
+    }
+    h->sd_val.reserve((size_t)P * 8, 0, false);
+    gemm(h->sd_act[D].as<double>(), h->n[D], h->Wrow[D].as<double>(), h->Brow[D].as<double>(), h->sd_val.as<double>(), 1, 1,
+         h->n[D], 0);
+    skips_into(D, h->sd_val.as<double>(), 1, 1);
+    CK(cudaGetLastError());
+}
+
+}  // namespace
+
+int am_seed_dichotomy(am_handle *h, const void *const *W, const void *const *B, const void *const *TM, const int *tm_shapes,
+                      int n_tm, const void *w_extra, const void *b_extra, int n_extra, double iso, int64_t init_num,
+                      int64_t try_pts_num, double ball_radius, int iter_max, double avg_eps, uint64_t seed,
+                      am_seed_report *report)
+{
+    if (!h || !W || !B || init_num < 1 || try_pts_num < 2 || !(ball_radius > 0.0) || iter_max < 0 ||
+        (n_tm > 0 && (!TM || !tm_shapes)) || init_num > (1 << 22) || try_pts_num > (1 << 22)) {
+        if (h) h->err = "am_seed_dichotomy: bad argument";
+        return AM_ERR_ARG;
+    }
+    if (n_extra != h->E) {
+        h->err = "am_seed_dichotomy: the number of extra constraints differs from am_create";
+        return AM_ERR_ARG;
+    }
+    try {
+        cudaStream_t st = h->stream;
+        CK(cudaDeviceSynchronize());
+        const auto t0 = std::chrono::steady_clock::now();
+        load_weights(h, W, B, TM, tm_shapes, n_tm);
+        {
+            auto we = fetch_real(w_extra, (size_t)h->E * 3, h->f64);
+            auto be = fetch_real(b_extra, (size_t)h->E, h->f64);
+            std::vector<double> ex((size_t)h->E * 4 + 4, 0.0);
+            for (int e = 0; e < h->E; ++e) {
+                ex[4 * e + 0] = we[3 * e + 0]; ex[4 * e + 1] = we[3 * e + 1]; ex[4 * e + 2] = we[3 * e + 2];
+                ex[4 * e + 3] = be[e];
+            }
+            upload(h->extra, ex.data(), ex.size() * 8, st);
+            CK(cudaStreamSynchronize(st));
+        }
+        const int N = (int)init_num, T = (int)try_pts_num;
+        h->sd_pts.reserve((size_t)T * 24, 0, false);
+        h->sd_valid.reserve((size_t)T * 4, 0, false);
+        h->sd_flags.reserve((size_t)T * 8, 0, false);     // is_pos | is_neg
+        h->sd_offs.reserve((size_t)T * 8, 0, false);
+        h->sd_lists.reserve((size_t)T * 8, 0, false);
+        h->sd_pos.reserve((size_t)N * 24, 0, false);
+        h->sd_neg.reserve((size_t)N * 24, 0, false);
+        h->sd_mid.reserve((size_t)N * 24, 0, false);
+        h->sd_err.reserve((size_t)N * 8 + 64, 0, false);
+        h->sd_tot.reserve(64);
+        h->sd_keys.reserve((size_t)N * h->kw * 4, 0, false);
+        uint32_t *is_pos = h->sd_flags.as<uint32_t>(), *is_neg = is_pos + T;
+        uint32_t *off_pos = h->sd_offs.as<uint32_t>(), *off_neg = off_pos + T;
+        int *pos_list = h->sd_lists.as<int>(), *neg_list = pos_list + T;
+        unsigned long long *tot = h->sd_tot.as<unsigned long long>();
+        unsigned long long h_tot[2];
+        int n_have = 0, rounds = 0;
+        const unsigned tb = (unsigned)((T + 255) / 256);
+        while (n_have < N) {
+            if (rounds >= 4096)
+                throw CudaFail{"no pair of trial points with opposite signs of f - iso within 4096 rounds (the reference "
+                               "raises after time_out, backend/main.py:276-277)"};
+            seed_sample_kernel<<<tb, 256, 0, st>>>(h->sd_pts.as<double>(), h->sd_valid.as<int>(), T, ball_radius,
+                                                   h->extra.as<double>(), h->E, seed, (uint32_t)rounds);
+            ++h->stats.n_launches;
+            seed_forward(h, h->sd_pts.as<double>(), T, nullptr);
+            seed_classify_kernel<<<tb, 256, 0, st>>>(h->sd_val.as<double>(), h->sd_valid.as<int>(), T, iso, is_pos, is_neg);
+            ++h->stats.n_launches;
+            h->scan(is_pos, off_pos, T, tot);
+            h->scan(is_neg, off_neg, T, tot + 1);
+            CK(cudaMemcpyAsync(h_tot, tot, 16, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const long long n_pos = (long long)h_tot[0], n_neg = (long long)h_tot[1];
+            if (n_pos > 0 && n_neg > 0) {
+                const long long n_take = std::min<long long>(N - n_have, n_pos * n_neg);
+                seed_lists_kernel<<<tb, 256, 0, st>>>(is_pos, off_pos, is_neg, off_neg, T, pos_list, neg_list);
+                seed_pairs_kernel<<<(unsigned)((n_take + 255) / 256), 256, 0, st>>>(
+                    h->sd_pts.as<double>(), pos_list, neg_list, (int)n_pos, (int)n_neg, (int)n_take, n_have,
+                    splitmix64(seed ^ (0xA5A5A5A5ull + (uint64_t)rounds)), h->sd_pos.as<double>(), h->sd_neg.as<double>());
+                h->stats.n_launches += 2;
+                n_have += (int)n_take;
+            }
+            ++rounds;
+        }
+        // bisection (reference backend/main.py:314-326): stop when the MEAN |f - iso| over the pairs is below avg_eps
+        int it = 0;
+        double avg = 0.0;
+        bool evaluated = false;
+        const unsigned nb = (unsigned)((N + 255) / 256);
+        for (; it < iter_max; ++it) {
+            seed_mid_kernel<<<(unsigned)((3 * N + 255) / 256), 256, 0, st>>>(h->sd_pos.as<double>(), h->sd_neg.as<double>(),
+                                                                           h->sd_mid.as<double>(), 3 * N);
+            seed_forward(h, h->sd_mid.as<double>(), N, h->sd_keys.as<uint32_t>());
+            seed_err_kernel<<<1, 1024, 0, st>>>(h->sd_val.as<double>(), iso, N, h->sd_err.as<double>());
+            h->stats.n_launches += 2;
+            double h_err = 0.0;
+            CK(cudaMemcpyAsync(&h_err, h->sd_err.p, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            avg = h_err / N;
+            evaluated = true;
+            if (avg < avg_eps) break;
+            seed_bisect_kernel<<<nb, 256, 0, st>>>(h->sd_val.as<double>(), iso, h->sd_mid.as<double>(), h->sd_pos.as<double>(),
+                                                   h->sd_neg.as<double>(), N);
+            ++h->stats.n_launches;
+            evaluated = false;
+        }
+        if (!evaluated) {      // iter_max reached (or zero): the points are the last midpoints, their states still missing
+            seed_mid_kernel<<<(unsigned)((3 * N + 255) / 256), 256, 0, st>>>(h->sd_pos.as<double>(), h->sd_neg.as<double>(),
+                                                                           h->sd_mid.as<double>(), 3 * N);
+            seed_forward(h, h->sd_mid.as<double>(), N, h->sd_keys.as<uint32_t>());
+            seed_err_kernel<<<1, 1024, 0, st>>>(h->sd_val.as<double>(), iso, N, h->sd_err.as<double>());
+            double h_err = 0.0;
+            CK(cudaMemcpyAsync(&h_err, h->sd_err.p, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            avg = h_err / N;
+        }
+        CK(cudaStreamSynchronize(st));
+        h->n_stored_seeds = N;
+        if (report) {
+            report->n_points = N;
+            report->rounds = rounds;
+            report->iterations = it;
+            report->avg_abs_error = avg;
+            report->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+    } catch (const CudaFail &f) {
+        h->err = "am_seed_dichotomy: " + f.msg;
+        return f.code;
+    }
+    return AM_OK;
+}
+
+int64_t am_num_seeds(const am_handle *h) { return h ? h->n_stored_seeds : 0; }
+
+int am_copy_seeds(const am_handle *h, double *points, uint8_t *states_bool)
+{
+    if (!h || h->n_stored_seeds < 1) return AM_ERR_STATE;
+    const size_t N = (size_t)h->n_stored_seeds;
+    cudaError_t e = cudaSuccess;
+    if (points) e = cudaMemcpy(points, h->sd_mid.p, N * 24, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && states_bool) {
+        std::vector<uint32_t> keys(N * h->kw);
+        e = cudaMemcpy(keys.data(), h->sd_keys.p, keys.size() * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < N && e == cudaSuccess; ++i)
+            for (int j = 0; j < h->L; ++j) states_bool[i * h->L + j] = (keys[i * h->kw + (j >> 5)] >> (j & 31)) & 1u;
+    }
+    return e == cudaSuccess ? AM_OK : AM_ERR_CUDA;
+}
+
 int am_set_shard_p2p(am_handle *h, int rank, int world, am_allgather_fn fn, void *user)
 {
     if (!h) return AM_ERR_ARG;
@@ -1797,13 +2125,14 @@ int am_set_shard_p2p(am_handle *h, int rank, int world, am_allgather_fn fn, void
         if (const char *e = getenv("AM_B200_XCHG_MIB")) mib = std::max(1.0, atof(e));
         if (const char *e = getenv("AM_B200_XCHG_TIMEOUT_MS")) h->xtimeout_ns = (unsigned long long)(atof(e) * 1e6);
         XchgLayout lay{};
-        lay.cap_corners = (int)std::min<double>(mib * (1 << 20) / 32.0, double(1 << 28));
-        lay.cap_states = lay.cap_corners / 3;
+        lay.cap_corners = (int)std::min<double>(mib * (1 << 20) / 28.0, double(1 << 28));
         lay.region_bytes = (lay.xyz_off() + (size_t)lay.cap_corners * 24 + 255) & ~size_t(255);
-        lay.mask_cap = 1 << 22;
+        lay.mask_cap = 1 << 21;
         if (const char *e = getenv("AM_B200_XCHG_LEVEL_STATES")) lay.mask_cap = std::max(1024, atoi(e));
         lay.mask_base = XCHG_CTRL_BYTES + (size_t)world * lay.region_bytes;
-        const size_t total = lay.mask_base + (size_t)world * lay.mask_cap * 4;
+        lay.cnt_base = lay.mask_base + (size_t)world * lay.mask_cap * 4;
+        lay.where_base = lay.cnt_base + (size_t)lay.mask_cap * 4;
+        const size_t total = lay.where_base + (size_t)lay.mask_cap * 8;
         CK(cudaMalloc(&h->xblock, total));
         CK(cudaMemset(h->xblock, 0, total));
         CK(cudaDeviceSynchronize());
@@ -1856,8 +2185,11 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
              const void *b_extra, int n_extra, double iso, int flip_insideout, void *user_stream)
 {
     if (!h) return AM_ERR_ARG;
-    if (!W || !B || !states || !points || n_seeds < 1 || (n_tm > 0 && (!TM || !tm_shapes))) {
-        h->err = "am_march: null argument or no seed states";
+    const bool stored = (states == nullptr && points == nullptr);      // seeds of the last am_seed_dichotomy
+    if (stored) n_seeds = h->n_stored_seeds;
+    if (!W || !B || (!stored && (!states || !points)) || n_seeds < 1 || (n_tm > 0 && (!TM || !tm_shapes))) {
+        h->err = stored ? "am_march: no stored seeds (call am_seed_dichotomy first)"
+                        : "am_march: null argument or no seed states";
         return AM_ERR_ARG;
     }
     if (n_extra != h->E) {
@@ -1880,6 +2212,7 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         h->spans.clear();
         h->stats = am_stats{};
         h->host_wait_s = 0.0;
+        h->span_scale = h->trace_every;
         const auto host_t0 = std::chrono::steady_clock::now();
         cudaEvent_t e_begin = h->ev();
         load_weights(h, W, B, TM, tm_shapes, n_tm);
@@ -1894,7 +2227,8 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
             upload(h->extra, ex.data(), ex.size() * 8, st);
             CK(cudaStreamSynchronize(st));
         }
-        auto pts = fetch_real(points, (size_t)n_seeds * 3, h->f64);
+        std::vector<double> pts;
+        if (!stored) pts = fetch_real(points, (size_t)n_seeds * 3, h->f64);
         h->n_states = 0;
         h->level_begin.clear();
         h->prev_resident = false;
@@ -1917,13 +2251,14 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         CK(cudaMemsetAsync(h->fs_ticket.p, 0, 64, st));                          // cleared here in case a march failed
         CK(cudaMemsetAsync(h->bal_loads.p, 0, XCHG_MAX_WORLD * 8, st));
         CK(cudaMemsetAsync(h->xcursor.p, 0, 64, st));
-        insert_seeds(h, states, pts.data(), n_seeds);
+        insert_seeds(h, stored ? nullptr : states, pts.data(), n_seeds);
         h->stats.n_seeds = n_seeds;
         h->stats.n_unique_seeds = h->n_states;
         long long lb = 0, le = h->n_states;
         while (le > lb) {
             h->level_begin.push_back(lb);
             h->stats.max_level_states = std::max<int64_t>(h->stats.max_level_states, le - lb);
+            h->trace_level = ((h->level_begin.size() - 1) % (size_t)h->trace_every) == 0;
             process_level(h, lb, le, iso, flip_insideout);
             lb = le;
             le = h->n_states;
@@ -2291,6 +2626,8 @@ int am_debug_planes(am_handle *h, const uint8_t *states, int64_t n, double iso, 
         h->ensure_chunk_scratch((size_t)n);
         h->ev_used = 0;
         h->spans.clear();
+        h->trace_level = true;
+        h->span_scale = 1;
         h->compose_chunk(h->xkeys.as<uint32_t>(), (int)n, iso, h->planes.as<double>(), nullptr, nullptr, (int)n, nullptr);
         CK(cudaStreamSynchronize(st));
         std::vector<double> p1((size_t)h->n1 * 4), pl((size_t)n * h->R * 4), eq((size_t)n * 4);

@@ -60,6 +60,7 @@ struct ClipArgs {
     int *out_edges;           // [S][VSLOTS]
     double *out_verts;        // [S][VSLOTS][3]
     unsigned long long *counters;
+    int tile_stride, tile_offset, tile;   // chained launches (compose.cuh chain_position); stride <= 1: the whole list
 };
 
 __device__ __forceinline__ double det3(double a, double b, double c, double d, double e, double f, double g, double h,
@@ -93,6 +94,7 @@ __device__ __forceinline__ void clip_cp16(void *smem, const void *gmem)
 template <int MINB, int RPL, int DEPTH>
 __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipArgs a)
 {
+    pdl_enter();
     extern __shared__ __align__(16) double s_ring[];  // [warp][DEPTH][RPL][32 lanes][4]: plane rows in flight
     __shared__ double s_pl[CLIP_WARPS][VSLOTS][4];   // plane of every polygon edge
     __shared__ __align__(16) double s_vx[CLIP_WARPS][VSLOTS + 4][4];   // vertex j = edge j ^ edge j+1 (x, y, z, -);
@@ -101,7 +103,8 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
     __shared__ uint32_t s_key[CLIP_WARPS][CLIP_KEY_WORDS];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int slot = blockIdx.x * CLIP_WARPS + wib;
+    const int li = blockIdx.x * CLIP_WARPS + wib;
+    const int slot = (a.tile_stride <= 1) ? li : ((li / a.tile) * a.tile_stride + a.tile_offset) * a.tile + (li % a.tile);
     if (slot >= a.S) return;
     const int s = a.idx ? a.idx[slot] : slot;
     double(*pl)[4] = s_pl[wib];
@@ -165,10 +168,25 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
         k = 4;
     }
     __syncwarp();
-    if (lane < 4) {   // padding slots
-        vx[k + lane][0] = vx[0][0]; vx[k + lane][1] = vx[0][1]; vx[k + lane][2] = vx[0][2];
-    }
-    __syncwarp();
+    // Bounding sphere of the current polygon (centre = vertex mean, radius inflated by 1e-6 + 1e-12): a plane whose
+    // signed value at the centre is <= -|a| R has no vertex on its positive side, which rejects almost every row
+    // with 8 FP64 operations instead of 4 per vertex.  Conservative: a row is only ever rejected when the exact
+    // predicate below would reject it as well, so the result does not depend on the filter.
+    double bcx = 0.0, bcy = 0.0, bcz = 0.0, bR2 = 0.0;
+    auto update_bound = [&]() {
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (int j = 0; j < k; ++j) { sx += vx[j][0]; sy += vx[j][1]; sz += vx[j][2]; }
+        const double inv_k = (k > 0) ? 1.0 / (double)k : 0.0;
+        bcx = sx * inv_k; bcy = sy * inv_k; bcz = sz * inv_k;
+        double r2 = 0.0;
+        for (int j = 0; j < k; ++j) {
+            const double dx = vx[j][0] - bcx, dy = vx[j][1] - bcy, dz = vx[j][2] - bcz;
+            r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+        }
+        const double r = sqrt(r2) * (1.0 + 1e-6) + 1e-12 * (1.0 + fabs(bcx) + fabs(bcy) + fabs(bcz));
+        bR2 = r * r;
+    };
+    update_bound();
 
     // per-warp ring of DEPTH blocks of RPL * 32 rows: the next DEPTH-1 blocks are in flight without holding registers
     double *ring = s_ring + (size_t)wib * DEPTH * (RPL * 32) * 4;
@@ -234,11 +252,8 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
             }
             __syncwarp();
             k = knew;
-            if (lane < 4) {   // refresh the padding slots
-                vx[k + lane][0] = vx[0][0]; vx[k + lane][1] = vx[0][1]; vx[k + lane][2] = vx[0][2];
-            }
-            __syncwarp();
         }
+        update_bound();
     };
     // The constraints come in three contiguous row segments (layer-1 rows shared by all states, the
     // state's own rows, the extra constraints); each segment is streamed in 64-row blocks with a running
@@ -321,20 +336,13 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
                 p[h][2] = live ? __hiloint2double(__double2hiint(hi[h].x) ^ flipbit, __double2loint(hi[h].x)) : 0.0;
                 p[h][3] = live ? __hiloint2double(__double2hiint(hi[h].y) ^ flipbit, __double2loint(hi[h].y)) : 0.0;
             }
-            // Fast filter: d_j * rs > EPS needs d_j > 0 (rs >= 0; NaN compares false either way), so a plane
-            // with no vertex on its positive side cannot cut.  Slots k..k+3 repeat vertex 0, so the loop runs
-            // unguarded in steps of four; every vertex load serves both rows of the lane.
-            for (int j = 0; j < k; j += 4) {
+            // Fast filter (see update_bound): d_j = t + a . (v_j - c) <= t + |a| R, and d_j * rs > EPS needs d_j > 0
+            // (rs >= 0; NaN compares false either way), so t <= 0 and t^2 >= |a|^2 R^2 means the plane cannot cut.
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double2 xy = *reinterpret_cast<const double2 *>(&vx[j + u][0]);
-                    const double z = vx[j + u][2];
-#pragma unroll
-                    for (int h = 0; h < RPL; ++h) {
-                        const double d = p[h][0] * xy.x + p[h][1] * xy.y + p[h][2] * z + p[h][3];
-                        pos[h] |= (d > 0.0);
-                    }
-                }
+            for (int h = 0; h < RPL; ++h) {
+                const double t = p[h][0] * bcx + p[h][1] * bcy + p[h][2] * bcz + p[h][3];
+                const double aa = p[h][0] * p[h][0] + p[h][1] * p[h][1] + p[h][2] * p[h][2];
+                pos[h] = (t > 0.0) || (t * t < aa * bR2);
             }
             bool any_pos = false;
 #pragma unroll

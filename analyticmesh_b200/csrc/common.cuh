@@ -47,6 +47,34 @@ __host__ __device__ inline uint64_t word_mix(uint32_t w, uint32_t v)
 
 __device__ __forceinline__ uint32_t slot_fp(uint64_t h) { return uint32_t(h >> 32); }
 
+// Programmatic dependent launch: the kernels of a BFS level form one long dependency chain of small launches, so
+// the launch latency between two of them is paid ~25 times per level.  A kernel launched with the
+// programmatic-stream-serialization attribute may be scheduled while its predecessor still runs; it must call
+// pdl_enter() before it touches global memory (griddepcontrol.wait returns once the predecessor grid has
+// completed and its writes are visible).  launch_dependents is issued first so that the kernel after this one
+// can be scheduled early as well.
+__device__ __forceinline__ void pdl_wait()
+{
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+// The successor may be scheduled once every CTA of this grid has executed this (or exited).  Short kernels issue
+// it at once; persistent kernels issue it when their work is done -- a successor that becomes resident early
+// only holds registers and shared memory that the running kernels (this one, or ITS successor's predecessor)
+// still need: measured, digit kernel at 2 instead of 3 CTAs/SM because the next GEMM's CTAs sat next to it.
+__device__ __forceinline__ void pdl_trigger()
+{
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_enter()
+{
+    pdl_trigger();
+    pdl_wait();
+}
+
 // first activation bit of every hidden layer (kernel parameter)
 constexpr int MAX_LAYERS = 64;
 struct LayerOffs {

@@ -323,6 +323,7 @@ __global__ void classify_scatter_kernel(const int *via_edge, const int *parent, 
                                         LayerOffs lo, BucketBase bb, int *bucket, int *cursor, int *perm,
                                         const uint8_t *owner, int rank)
 {
+    pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int e = via_edge[lb + s], p = parent[lb + s];
@@ -383,7 +384,15 @@ struct EquArgs {
     const int *parent;
     int lb, prev_lb, D;
     const double *alt_in;     // rows of the last hidden layer of the previous level's state 0
+    // chained launches: this launch handles the list positions of tiles tile_offset, tile_offset + tile_stride, ...
+    int tile_stride, tile_offset, tile;
 };
+
+// i-th position handled by a chained launch -> position in the whole list (tiles of `tile` positions dealt round-robin)
+__device__ __forceinline__ int chain_position(int i, int tile, int stride, int offset)
+{
+    return (stride <= 1) ? i : ((i / tile) * stride + offset) * tile + (i % tile);
+}
 
 __device__ __forceinline__ double masked_chain(const double *w, const double *rows, const uint32_t *key, int bit0,
                                                int K, int c)
@@ -413,9 +422,11 @@ __device__ __forceinline__ double masked_chain(const double *w, const double *ro
 
 __global__ void equ_kernel(const EquArgs a)
 {
+    pdl_enter();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.S * 4) return;
-    const int s = a.idx ? a.idx[t >> 2] : (t >> 2), c = t & 3;
+    const int pos = chain_position(t >> 2, a.tile, a.tile_stride, a.tile_offset);
+    if (pos >= a.S) return;
+    const int s = a.idx ? a.idx[pos] : pos, c = t & 3;
     const uint32_t *key = a.keys + (size_t)s * a.kw;
     const double *rows = a.in + (size_t)s * a.in_stride;
     if (a.bucket != nullptr && a.bucket[s] == a.D) rows = a.alt_in + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.in_stride;

@@ -96,6 +96,7 @@ struct LevelArgs {
     // fused winner kernel (xchg.cuh winners_scan_kernel): id offset = win_off64[s / FS_TILE] + win_base64[s], low half
     // = index among the level's children, high half = index among its free children (dealt by `cuts`)
     const unsigned long long *win_base64, *win_off64;
+    int cap_states;                       // finalize: arena capacity (children beyond it are skipped; the host re-runs)
     const int *cuts;                      // [world + 1] or nullptr: free child f -> rank r with cuts[r] <= f < cuts[r + 1]
     int free_below_bit;                   // a child is free when its flipped neuron index is below this (first bit of layer 2)
     int n_ranks;
@@ -106,10 +107,14 @@ __device__ __forceinline__ int key_hash_owner(uint64_t h, int world) { return in
 // candidate (parent sid, edge slot j) <-> 31-bit index within the level
 __device__ __forceinline__ uint32_t cand_index(int s_local, int j) { return (uint32_t(s_local) << 5) | uint32_t(j); }
 
-// phase 1: one group of G lanes per parent state, its edges in order
+// phase 1: one group of G lanes per parent state.  Lane j owns candidate j (the state across polygon edge j): it
+// hashes and probes on its own, so the k dependent probe chains of a state run side by side instead of one
+// after the other; only a fingerprint match needs the whole group (cooperative full-key compare), and those are
+// resolved one at a time.  cand_slot[s][j] is written for j < k only (nobody reads the rest).
 template <int G>
 __global__ void expand_insert_kernel(const LevelArgs a)
 {
+    pdl_enter();
     cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (s >= a.S) return;
@@ -120,85 +125,80 @@ __global__ void expand_insert_kernel(const LevelArgs a)
     const uint4 *key4 = reinterpret_cast<const uint4 *>(key);
     const uint64_t h0 = a.hsum[sid];
     int ncand = 0;
-    for (int j = 0; j < VSLOTS; ++j) {
-        int result = NO_SLOT;
+    for (int j0 = 0; j0 < k; j0 += G) {
+        const int j = j0 + (int)tile.thread_rank();
+        int result = NO_SLOT, e = -1;
+        bool active = false;
+        uint32_t fp = 0, slot = 0;
+        uint64_t mine = 0;
         if (j < k) {
-            const int e = a.face_edges[fo + j];
+            e = a.face_edges[fo + j];
             if (e >= 0 && e < a.L) {
-                ++ncand;
                 const uint64_t h = hash_flip(h0, key, e);
-                const uint32_t fp = slot_fp(h);
-                const uint64_t mine = (uint64_t(fp) << 32) | CAND_TAG | cand_index(s, j);
-                uint32_t slot = uint32_t(h) & a.table.mask;
-                const bool ours = (a.world <= 1) || key_hash_owner(h, a.world) == a.rank;
-                while (ours) {
-                    unsigned long long v = 0;
-                    if (tile.thread_rank() == 0) {
-                        v = a.table.slots[slot];
-                        if (v == SLOT_EMPTY) v = atomicCAS(a.table.slots + slot, SLOT_EMPTY, mine);
+                fp = slot_fp(h);
+                mine = (uint64_t(fp) << 32) | CAND_TAG | cand_index(s, j);
+                slot = uint32_t(h) & a.table.mask;
+                active = (a.world <= 1) || key_hash_owner(h, a.world) == a.rank;
+            } else {
+                e = -1;
+            }
+        }
+        ncand += __popc(tile.ballot(e >= 0));
+        while (tile.any(active)) {
+            unsigned long long v = 0;
+            bool pend = false;
+            if (active) {
+                for (;;) {                                   // probe until the slot is claimed or a fingerprint matches
+                    v = a.table.slots[slot];
+                    if (v == SLOT_EMPTY) {
+                        v = atomicCAS(a.table.slots + slot, SLOT_EMPTY, mine);
+                        if (v == SLOT_EMPTY) { result = int(slot); active = false; break; }
                     }
-                    v = tile.shfl(v, 0);
-                    if (v == SLOT_EMPTY) { result = int(slot); break; }        // claimed
-                    if (uint32_t(v >> 32) == fp) {
-                        const uint32_t low = uint32_t(v);
-                        bool same;
-                        if (low & CAND_TAG) {                                  // another candidate of this level
-                            const uint32_t ci = low & ~CAND_TAG;
-                            const int sid2 = a.lb + int(ci >> 5);
-                            const int e2 = a.face_edges[a.face_off[sid2] + (ci & 31u)];
-                            same = keys_equal<G>(tile, key4, e,
-                                                 reinterpret_cast<const uint4 *>(a.keys + (size_t)sid2 * a.kw), e2, a.kw4);
-                            if (same) {
-                                if (tile.thread_rank() == 0) atomicMin(a.table.slots + slot, mine);
-                                result = int(slot);
-                                break;
-                            }
-                        } else {                                               // an already visited state
-                            same = keys_equal<G>(tile, key4, e,
-                                                 reinterpret_cast<const uint4 *>(a.keys + (size_t)low * a.kw), -1, a.kw4);
-                            if (same) break;
-                        }
-                    }
+                    if (uint32_t(v >> 32) == fp) { pend = true; break; }
                     slot = (slot + 1) & a.table.mask;
                 }
             }
-        }
-        if (tile.thread_rank() == 0) a.cand_slot[(size_t)s * VSLOTS + j] = result;
-    }
-    if (tile.thread_rank() == 0 && ncand) atomicAdd(a.counters + CNT_CANDIDATES, (unsigned long long)ncand);
-}
-
-// phase 2a: winners per parent (thread per parent)
-// Also histograms the children by the hidden layer of their flipped neuron (bucket of the NEXT level's
-// incremental composition, compose.cuh classify_kernel) so that the host learns the next level's launch
-// sizes from the same read-back as n_new.  Sharded mode: only children this rank will own are counted.
-__global__ void count_winners_kernel(const LevelArgs a, LayerOffs lo, int *next_counts, int rank)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.S) return;
-    uint32_t n = 0;
-    const long long fo = a.face_off[a.lb + s];
-    const bool mine = (a.owner == nullptr) || (a.owner[a.lb + s] == rank);
-    for (int j = 0; j < VSLOTS; ++j) {
-        const int slot = a.cand_slot[(size_t)s * VSLOTS + j];
-        if (slot == NO_SLOT) continue;
-        if (uint32_t(a.table.slots[slot]) == (CAND_TAG | cand_index(s, j))) {
-            ++n;
-            if (mine) {
-                const int e = a.face_edges[fo + j];
-                int b = 1;
-                while (b < lo.D && e >= lo.off[b + 1]) ++b;
-                atomicAdd(next_counts + b, 1);
+            unsigned pm = tile.ballot(pend);
+            while (pm) {                                     // full-key compares, one candidate at a time
+                const int src = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const unsigned long long vs = tile.shfl(v, src);
+                const int es = tile.shfl(e, src);
+                const uint32_t low = uint32_t(vs);
+                bool same;
+                if (low & CAND_TAG) {                        // another candidate of this level
+                    const uint32_t ci = low & ~CAND_TAG;
+                    const int sid2 = a.lb + int(ci >> 5);
+                    const int e2 = a.face_edges[a.face_off[sid2] + (ci & 31u)];
+                    same = keys_equal<G>(tile, key4, es, reinterpret_cast<const uint4 *>(a.keys + (size_t)sid2 * a.kw), e2,
+                                         a.kw4);
+                } else {                                     // an already visited state
+                    same = keys_equal<G>(tile, key4, es, reinterpret_cast<const uint4 *>(a.keys + (size_t)low * a.kw), -1,
+                                         a.kw4);
+                }
+                if ((int)tile.thread_rank() == src) {
+                    if (same) {
+                        if (low & CAND_TAG) {                // same key: the smaller candidate index wins the slot
+                            atomicMin(a.table.slots + slot, mine);
+                            result = int(slot);
+                        }
+                        active = false;
+                    } else {
+                        slot = (slot + 1) & a.table.mask;
+                    }
+                }
             }
         }
+        if (j < k) a.cand_slot[(size_t)s * VSLOTS + j] = result;
     }
-    a.nwin[s] = n;
+    if (tile.thread_rank() == 0 && ncand) atomicAdd(a.counters + CNT_CANDIDATES, (unsigned long long)ncand);
 }
 
 // phase 2b: winners append their state (group of G lanes per parent)
 template <int G>
 __global__ void finalize_kernel(const LevelArgs a)
 {
+    pdl_enter();
     cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     if (s >= a.S) return;
@@ -228,6 +228,11 @@ __global__ void finalize_kernel(const LevelArgs a)
             if (uint32_t(v) != (CAND_TAG | cand_index(s, j))) continue;
         }
         const int e = a.face_edges[fo + j];
+        if (nid >= a.cap_states) {              // speculative launch with too small an arena: skipped, re-run by the host
+            ++nid;
+            if (a.cuts != nullptr && e < a.free_below_bit) ++fidx;
+            continue;
+        }
         uint4 *dst = reinterpret_cast<uint4 *>(a.keys_w + (size_t)nid * a.kw);
         for (int q = tile.thread_rank(); q < a.kw4; q += G) {
             uint4 x = key4[q];

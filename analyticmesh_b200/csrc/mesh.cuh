@@ -84,6 +84,7 @@ struct CompactArgs {
 
 __global__ void compact_faces_kernel(const CompactArgs a)
 {
+    pdl_enter();
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= a.S) return;

@@ -110,6 +110,7 @@ __device__ __forceinline__ bool fused_scan_block(const T (&v)[FS_ITEMS], T (&exc
 // stand-alone form: local[i] = block-local exclusive prefix of in[i]
 __global__ void __launch_bounds__(FS_THREADS) scan_local_kernel(const uint32_t *in, int n, uint32_t *local, FusedScan fs)
 {
+    pdl_enter();
     const int base = blockIdx.x * FS_TILE + threadIdx.x * FS_ITEMS;
     uint32_t v[FS_ITEMS], e[FS_ITEMS];
 #pragma unroll

@@ -104,6 +104,7 @@ __device__ __forceinline__ const double *slice_rows_of(const SliceArgs &a, int s
 template <int SD>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a)
 {
+    pdl_enter();
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (slot >= a.S || (slot / SP_BS) % a.tile_stride != a.tile_offset) return;
@@ -202,6 +203,7 @@ __device__ __forceinline__ SliceMeta<NIT> slice_meta(const SliceArgs &a, int slo
 template <int SD, int NIT>
 __global__ void __launch_bounds__(128, 3) slice_rows_reg_kernel(const SliceArgs a)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int n_warps = gridDim.x * (blockDim.x >> 5);
     int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(128, 3) slice_rows_reg_kernel(const SliceArgs 
     if (slot >= a.S) return;
     SliceMeta<NIT> cur = slice_meta<NIT>(a, slot, lane);
     while (slot < a.S) {
+        if (slot + n_warps >= a.S) pdl_trigger();      // last state of this warp: the GEMM's CTAs may move in
         double v[NIT][4][4];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
@@ -404,6 +407,11 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
+    // barriers and TMEM are set up while the digit kernel before this launch is still running; nothing it wrote
+    // is touched before this point
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 
     if (warp == 0) {
         if (lane == 0) {
@@ -515,6 +523,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

@@ -5,11 +5,11 @@
 // on the rank that owns it; the key arena, the polygon CSR and the state numbering are replicated and stay
 // bit-identical on every rank; the visited set is sharded by key hash.  Two things cross the links per level:
 //
-//   polygons    the owner of a state PUSHES its polygon (edge ids + vertices, 28 B per corner, compacted) and a
-//               12-byte record {state, size, offset} into every peer's inbox with plain stores over NVLink;
-//               after one device-side barrier every rank scatters the sizes into state order, prefix-sums them
-//               and copies the polygons from its own inbox into the CSR -- the sizes and offsets never visit
-//               the host.  (Round 1: three ncclAllReduce over zero-padded buffers + a host sync per level.)
+//   polygons    the owner of a state PUSHES its polygon (edge ids + vertices, 28 B per corner, compacted), its size
+//               and its location {rank, offset} into every peer's block with plain stores over NVLink; after one
+//               device-side barrier every rank prefix-sums the sizes (already in state order) and copies the
+//               polygons from its own inbox into the CSR -- sizes and offsets never visit the host.
+//               (Round 1: three ncclAllReduce over zero-padded buffers + a host sync per level.)
 //   winners     neighbour candidates are de-duplicated by the rank that owns the candidate key's hash (a rank
 //               probes / inserts only 1/world of the candidates into its shard of the visited set); the 32-bit
 //               mask "which edge slots of state s discovered a new state" is pushed to every peer and OR-ed
@@ -18,10 +18,9 @@
 //
 // Every rank owns ONE exchange block (cudaMalloc, exported with cudaIpcGetMemHandle, opened by the peers):
 //     [0, XCHG_CTRL_BYTES)         control: arrive[src] epoch flags (one 128-byte line per source rank)
-//     world polygon regions        region r is written by rank r only:
-//                                  header (64 B: number of records) | records [cap_states] | edges [cap_corners]
-//                                  | vertices [cap_corners][3]
+//     world polygon regions        region r is written by rank r only: edges [cap_corners] | vertices [cap_corners][3]
 //     world mask regions           [mask_cap] uint32, region r written by rank r only
+//     sizes, locations             [mask_cap] int + [mask_cap] int2, entry s written by the owner of state s
 // A region is reused every level: a rank writes level l+1 only after the barrier that follows level l's winner
 // exchange, which every rank reaches only after it has consumed level l's polygons (stream order).
 #pragma once
@@ -41,13 +40,13 @@ struct XchgPeers {
 struct XchgLayout {
     size_t region_bytes;      // one polygon region
     size_t mask_base;         // offset of mask region 0
-    int cap_states;           // records per polygon region
+    size_t cnt_base;          // [mask_cap] int: polygon size per level-local state, written by the state's owner
+    size_t where_base;        // [mask_cap] int2: (source rank, corner offset in that rank's region)
     int cap_corners;          // corners per polygon region
-    int mask_cap;             // states per mask region (= widest level the sharded march accepts)
+    int mask_cap;             // states per level the sharded march accepts
     __host__ __device__ size_t region(int r) const { return XCHG_CTRL_BYTES + (size_t)r * region_bytes; }
-    __host__ __device__ size_t rec_off() const { return XCHG_HDR_BYTES; }
-    __host__ __device__ size_t edge_off() const { return (XCHG_HDR_BYTES + (size_t)cap_states * 12 + 15) & ~size_t(15); }
-    __host__ __device__ size_t xyz_off() const { return (edge_off() + (size_t)cap_corners * 4 + 15) & ~size_t(15); }
+    __host__ __device__ size_t edge_off() const { return 0; }
+    __host__ __device__ size_t xyz_off() const { return ((size_t)cap_corners * 4 + 15) & ~size_t(15); }
     __host__ __device__ size_t mask(int r) const { return mask_base + (size_t)r * mask_cap * 4; }
 };
 
@@ -64,6 +63,7 @@ __device__ __forceinline__ unsigned long long xchg_now_ns()
 // timeout_ns and raises the error counter instead of hanging the GPU.
 __global__ void xchg_barrier_kernel(XchgPeers p, uint32_t epoch, unsigned long long timeout_ns, unsigned long long *counters)
 {
+    pdl_enter();
     const int q = threadIdx.x;
     if (q < p.world) {
         __threadfence_system();
@@ -100,12 +100,11 @@ struct XchgPackArgs {
 
 __global__ void xchg_pack_kernel(const XchgPackArgs a)
 {
+    pdl_enter();
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const size_t reg = a.lay.region(a.p.rank);
-    if (blockIdx.x == 0 && threadIdx.x < a.p.world)
-        *reinterpret_cast<int *>(a.p.base[threadIdx.x] + reg) = a.n;
     if (i >= a.n) return;
+    const size_t reg = a.lay.region(a.p.rank);
     const int s = a.idx[i];
     int k = a.cnt[s];
     int off = 0;
@@ -126,35 +125,16 @@ __global__ void xchg_pack_kernel(const XchgPackArgs a)
         x = v[0]; y = v[1]; z = v[2];
     }
     for (int q = 0; q < a.p.world; ++q) {
-        unsigned char *r = a.p.base[q] + reg;
+        unsigned char *b = a.p.base[q];
         if (lane == 0) {
-            int *rec = reinterpret_cast<int *>(r + a.lay.rec_off()) + (size_t)i * 3;
-            rec[0] = s; rec[1] = k; rec[2] = off;
+            reinterpret_cast<int *>(b + a.lay.cnt_base)[s] = k;
+            reinterpret_cast<int2 *>(b + a.lay.where_base)[s] = make_int2(a.p.rank, off);
         }
         if (lane < k) {
-            reinterpret_cast<int *>(r + a.lay.edge_off())[off + lane] = e;
-            double *o = reinterpret_cast<double *>(r + a.lay.xyz_off()) + (size_t)(off + lane) * 3;
+            reinterpret_cast<int *>(b + reg + a.lay.edge_off())[off + lane] = e;
+            double *o = reinterpret_cast<double *>(b + reg + a.lay.xyz_off()) + (size_t)(off + lane) * 3;
             o[0] = x; o[1] = y; o[2] = z;
         }
-    }
-}
-
-// records of every source rank -> polygon size and location per level-local state (grid: x over records, y = source)
-__global__ void xchg_unpack_kernel(const unsigned char *own, XchgLayout lay, int S, int *cnt_all, int2 *where,
-                                   unsigned long long *counters)
-{
-    const int r = blockIdx.y;
-    const unsigned char *reg = own + lay.region(r);
-    const int n = *reinterpret_cast<const int *>(reg);
-    const int *rec = reinterpret_cast<const int *>(reg + lay.rec_off());
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int s = rec[(size_t)i * 3], k = rec[(size_t)i * 3 + 1], off = rec[(size_t)i * 3 + 2];
-        if (s < 0 || s >= S || k < 0 || k > VSLOTS) {
-            atomicAdd(counters + CNT_XCHG_ERROR, 1ull << 16);
-            continue;
-        }
-        cnt_all[s] = k;
-        where[s] = make_int2(r, off);
     }
 }
 
@@ -175,6 +155,7 @@ struct XchgCompactArgs {
 
 __global__ void xchg_compact_kernel(const XchgCompactArgs a)
 {
+    pdl_enter();
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= a.S) return;
@@ -199,10 +180,12 @@ __global__ void xchg_compact_kernel(const XchgCompactArgs a)
 // thread per parent state: bit j of the mask = candidate (s, j) was inserted by THIS rank and won its slot
 __global__ void xchg_push_masks_kernel(const LevelArgs a, XchgPeers p, XchgLayout lay)
 {
+    pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.S) return;
     uint32_t m = 0;
-    for (int j = 0; j < VSLOTS; ++j) {
+    const int k = int(a.face_off[a.lb + s + 1] - a.face_off[a.lb + s]);
+    for (int j = 0; j < k; ++j) {
         const int slot = a.cand_slot[(size_t)s * VSLOTS + j];
         if (slot != NO_SLOT && uint32_t(a.table.slots[slot]) == (CAND_TAG | cand_index(s, j))) m |= 1u << j;
     }
@@ -240,6 +223,7 @@ struct WinArgs {
 template <bool SHARDED_TABLE>
 __global__ void __launch_bounds__(FS_THREADS) winners_scan_kernel(const LevelArgs a, const WinArgs w)
 {
+    pdl_enter();
     if (blockIdx.x == 0 && (int)threadIdx.x < w.n_zero_a) w.zero_a[threadIdx.x] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && w.zero_b) *w.zero_b = 0;
     const int s0 = blockIdx.x * FS_TILE + threadIdx.x * FS_ITEMS;

@@ -24,6 +24,7 @@ _float_type = ""
 _nodesnum = None
 _arc_table = None
 _num_extra = 0
+_env_serial = 0         # bumped by every Init: lets a caching caller notice that the environment was replaced
 
 
 class AmStats(ctypes.Structure):
@@ -40,7 +41,7 @@ class AmStats(ctypes.Structure):
 EXPORTS = ("am_create", "am_march", "am_combine", "am_export", "am_destroy", "am_get_stats", "am_last_error",
            "am_key_words", "am_state_len", "am_copy_states", "am_copy_faces", "am_copy_mesh", "am_load_weights",
            "am_debug_planes", "am_compose_profile", "am_kernel_profile", "am_gemm_variant", "am_fp64_peak_tflops", "am_set_shard", "am_nccl_unique_id",
-           "am_set_shard_nccl", "am_set_shard_p2p", "am_gather_states", "am_digest", "am_edge_incidence", "am_ply_parse_faces",
+           "am_set_shard_nccl", "am_set_shard_p2p", "am_seed_dichotomy", "am_copy_seeds", "am_num_seeds", "am_gather_states", "am_digest", "am_edge_incidence", "am_ply_parse_faces",
            "am_ply_pack_faces")
 
 
@@ -132,7 +133,15 @@ def Init(float_type, nodesnum, arc_table, num_extra_constraints):
                          at.ctypes.data_as(ctypes.c_void_p), at.shape[0], at.shape[1], int(num_extra_constraints))
     if rc != 0:
         raise RuntimeError(f"Init failed ({rc}): {lib().am_last_error(None).decode()}")
+    global _env_serial
+    _env_serial += 1
     _handle, _float_type, _nodesnum, _arc_table, _num_extra = h, float_type, nodesnum, at.copy(), int(num_extra_constraints)
+
+
+def environment_id():
+    """0 when no environment is alive, else a number that changes with every Init (analyticmesh_b200.main uses it to
+    validate its environment cache against direct cuam.Init / cuam.Destroy calls)."""
+    return _env_serial if _handle is not None else 0
 
 
 def AnalyticMarching(weights, biases, states, points, arc_tm, w_extra_constraints, b_extra_constraints, iso,
@@ -158,11 +167,13 @@ def AnalyticMarching(weights, biases, states, points, arc_tm, w_extra_constraint
     _check(_shape(weights[0])[1] == 3, "weights[0].size(1) == 3")
     _check(_shape(weights[-1])[0] == 1, "weights.back().size(0) == 1")
     L -= 1
-    _check(len(_shape(states)) == 2 and _shape(states)[0] >= 1 and _shape(states)[1] == L,
-           "states must have shape (N >= 1, hidden_states_vector_len)")
-    _check(_dtype_name(states) == "bool", "states.dtype() == torch::kBool")
-    _check(_shape(points) == (_shape(states)[0], 3), "points must have shape (N, 3)")
-    _check(_dtype_name(points) == want, f"points must be {want}")
+    stored = states is None and points is None          # march from the seeds of the last seed_dichotomy()
+    if not stored:
+        _check(len(_shape(states)) == 2 and _shape(states)[0] >= 1 and _shape(states)[1] == L,
+               "states must have shape (N >= 1, hidden_states_vector_len)")
+        _check(_dtype_name(states) == "bool", "states.dtype() == torch::kBool")
+        _check(_shape(points) == (_shape(states)[0], 3), "points must have shape (N, 3)")
+        _check(_dtype_name(points) == want, f"points must be {want}")
     tm_shapes = []
     for tm in arc_tm:
         _check(len(_shape(tm)) == 2 and _dtype_name(tm) == want, "arc_tm entries must be 2-D of the Init dtype")
@@ -182,7 +193,8 @@ def AnalyticMarching(weights, biases, states, points, arc_tm, w_extra_constraint
            f"extra constraints must be {want}")
     tm_c = (ctypes.c_int * max(len(tm_shapes), 1))(*tm_shapes)
     rc = lib().am_march(_handle, _ptr_array(weights), _ptr_array(biases), _ptr_array(arc_tm), tm_c, len(arc_tm),
-                        _ptr(states), _ptr(points), ctypes.c_int64(_shape(states)[0]), _ptr(w_extra_constraints),
+                        None if stored else _ptr(states), None if stored else _ptr(points),
+                        ctypes.c_int64(0 if stored else _shape(states)[0]), _ptr(w_extra_constraints),
                         _ptr(b_extra_constraints), _shape(w_extra_constraints)[0], ctypes.c_double(float(iso)),
                         int(bool(flip_insideout)), ctypes.c_void_p(stream))
     _err(rc, "AnalyticMarching")
@@ -281,6 +293,47 @@ def mesh():
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
     _err(lib().am_copy_mesh(_handle, p(v), p(fs), p(fi)), "mesh")
     return v, fs, fi
+
+
+class AmSeedReport(ctypes.Structure):
+    _fields_ = [("n_points", ctypes.c_int64), ("rounds", ctypes.c_int64), ("iterations", ctypes.c_int64),
+                ("avg_abs_error", ctypes.c_double), ("seconds", ctypes.c_double)]
+
+
+def seed_dichotomy(weights, biases, arc_tm, w_extra_constraints, b_extra_constraints, iso, init_num=1024,
+                   try_pts_num=4096, init_ball_radius=1.0, iter_max=100, avg_eps=1e-3, seed=0):
+    """The surface-point initialiser on the device (include/am_b200.h: am_seed_dichotomy; reference
+    backend/main.py:252-326).  The seeds stay on the device: AnalyticMarching(states=None, points=None, ...) marches
+    from them; seeds() copies them out.  Returns the report dict."""
+    tm_shapes = []
+    for tm in arc_tm:
+        tm_shapes += list(_shape(tm))
+    tm_c = (ctypes.c_int * max(len(tm_shapes), 1))(*tm_shapes)
+    rep = AmSeedReport()
+    fn = lib().am_seed_dichotomy
+    fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_double, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_int,
+                                           ctypes.c_double, ctypes.c_uint64, ctypes.c_void_p]
+    _err(fn(_handle, _ptr_array(weights), _ptr_array(biases), _ptr_array(arc_tm), tm_c, len(arc_tm),
+            _ptr(w_extra_constraints), _ptr(b_extra_constraints), _shape(w_extra_constraints)[0], float(iso), int(init_num),
+            int(try_pts_num), float(init_ball_radius), int(iter_max), float(avg_eps), int(seed) & (2**64 - 1),
+            ctypes.byref(rep)), "seed_dichotomy")
+    return {n: getattr(rep, n) for n, _ in AmSeedReport._fields_}
+
+
+def seeds():
+    """(points (N, 3) float64, states (N, L) bool) found by the last seed_dichotomy()."""
+    L = lib().am_state_len(_handle)
+    fn = lib().am_copy_seeds
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    nfn = lib().am_num_seeds
+    nfn.argtypes = [ctypes.c_void_p]
+    nfn.restype = ctypes.c_int64
+    n = int(nfn(_handle))
+    pts = np.zeros((n, 3), dtype=np.float64)
+    st = np.zeros((n, L), dtype=np.uint8)
+    _err(fn(_handle, pts.ctypes.data_as(ctypes.c_void_p), st.ctypes.data_as(ctypes.c_void_p)), "seeds")
+    return pts, st.astype(bool)
 
 
 def gather_states(ids):

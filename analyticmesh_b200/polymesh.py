@@ -31,6 +31,18 @@ class PolyMesh:
             self.set_faces(faces or [])
             self.set_colors(colors or [])
 
+    @classmethod
+    def from_arrays(cls, vertices, face_sizes, face_index, colors=None):
+        """Build from flat arrays (no python lists): vertices (V, 3), face_sizes (F,), face_index (sum of sizes,) --
+        the layout cuam.mesh() returns, used by the voxel mode to merge the per-voxel meshes in memory."""
+        m = cls()
+        m._v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        m._cnt = np.ascontiguousarray(face_sizes, dtype=np.int32).reshape(-1)
+        m._idx = np.ascontiguousarray(face_index, dtype=np.int32).reshape(-1)
+        assert int(m._cnt.sum()) == len(m._idx)
+        m._col = np.zeros((0, 3), dtype=np.uint8) if colors is None else np.ascontiguousarray(colors, dtype=np.uint8)
+        return m
+
     # ------------------------------------------------------------------ storage
     def clear(self):
         self._v = np.zeros((0, 3), dtype=np.float32)

@@ -75,6 +75,7 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
  * states: n_seeds x L bytes (0/1, torch.bool layout); points: n_seeds x 3 reals;
  * w_extra: n_extra x 3, b_extra: n_extra (inside is w.x + b < 0).  n_extra must equal the
  * value given to am_create (the reference does not check this).
+ * states = points = NULL (n_seeds ignored): march from the seeds of the last am_seed_dichotomy call.
  * stream: a cudaStream_t (NULL = default stream).  Returns after the march has completed. */
 int am_march(am_handle *h, const void *const *W, const void *const *B, const void *const *TM,
              const int *tm_shapes, int n_tm, const uint8_t *states, const void *points, int64_t n_seeds,
@@ -116,6 +117,24 @@ int am_set_shard_nccl(am_handle *h, int rank, int world, const void *unique_id12
  * on every rank, e.g. torch.distributed.all_gather, and return 0.  Collective call. */
 typedef int (*am_allgather_fn)(void *user, const void *send, void *recv, int64_t bytes);
 int am_set_shard_p2p(am_handle *h, int rank, int world, am_allgather_fn fn, void *user);
+
+/* The surface-point initialiser on the device (csrc/seeds.cuh): replaces `dichotomy` + `init_within_ball` +
+ * `constraints_filter` + the state extraction of reference backend/main.py:252-326, 83-91, 70-80, 408-411.
+ * try_pts_num trial points per round are drawn in the ball by a counter-based generator keyed by `seed`, points of
+ * opposite sign of f - iso are paired without replacement, every pair is bisected until the mean |f - iso| is below
+ * avg_eps (or iter_max bisections).  The init_num points and their packed activation keys stay on the device:
+ * am_march(..., states = NULL, points = NULL, n_seeds = 0, ...) marches from them.  Deterministic in `seed`. */
+typedef struct am_seed_report {
+    int64_t n_points, rounds, iterations;
+    double avg_abs_error, seconds;
+} am_seed_report;
+int am_seed_dichotomy(am_handle *h, const void *const *W, const void *const *B, const void *const *TM,
+                      const int *tm_shapes, int n_tm, const void *w_extra, const void *b_extra, int n_extra,
+                      double iso, int64_t init_num, int64_t try_pts_num, double ball_radius, int iter_max,
+                      double avg_eps, uint64_t seed, am_seed_report *report);
+/* the stored seeds: points [n][3] double, states [n][L] bytes (0/1); either may be NULL.  Host pointers. */
+int am_copy_seeds(const am_handle *h, double *points, uint8_t *states_bool);
+int64_t am_num_seeds(const am_handle *h);
 
 int am_get_stats(const am_handle *h, am_stats *out);
 const char *am_last_error(const am_handle *h);   /* h may be NULL: error of the last failed am_create */

@@ -110,3 +110,42 @@ def test_batch_of_latent_shapes_reuses_the_environment(oracle_lib):
         assert rep["keys_equal"] and rep["loops_equal"] and rep["max_vertex_err"] < 1e-9, (k, rep)
         counts.append(eng["stats"]["n_faces"])
     assert len(set(counts)) > 1 or counts[0] > 0
+
+
+def test_native_dichotomy_seeds_on_the_device(oracle_lib):
+    """the surface-point initialiser as device code (csrc/seeds.cuh, am_seed_dichotomy) against the
+    behaviour of reference backend/main.py:252-326 -- init_num points inside the ball and the extra constraints, mean
+    |f - iso| below avg_eps, activation patterns equal to a float64 forward pass, deterministic in the seed -- and the
+    march from the stored seeds equals the march from the same seeds handed over as (states, points)."""
+    from analyticmesh_b200 import cuam
+    for name in ("chair", "skipnet", "chair_cube", "mlp3x256s_cube"):
+        case = build_case(name)
+        info = case["info"]
+        we, be = np.ascontiguousarray(case["w_extra"]).reshape(-1, 3), np.ascontiguousarray(case["b_extra"]).reshape(-1)
+        cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table, num_extra_constraints=len(be))
+        rep = cuam.seed_dichotomy(info.weights, info.biases, info.arc_tm, we, be, 0.0, init_num=300, try_pts_num=4096,
+                                  init_ball_radius=1.0, iter_max=100, avg_eps=1e-3, seed=5)
+        pts, st = cuam.seeds()
+        assert pts.shape == (300, 3) and st.shape == (300, info.state_len) and rep["n_points"] == 300
+        f, bits = info.forward(pts)
+        assert np.abs(f).mean() < 1e-3 and abs(np.abs(f).mean() - rep["avg_abs_error"]) < 1e-9, (name, rep)
+        assert int((bits != st).sum()) == 0, name
+        assert (np.square(pts).sum(1) < 1.0).all()
+        if len(be):
+            assert ((pts @ we.T + be) < 0).all()
+        cuam.seed_dichotomy(info.weights, info.biases, info.arc_tm, we, be, 0.0, init_num=300, seed=5)
+        assert np.array_equal(cuam.seeds()[0], pts)                       # same seed, same points
+        kw = dict(weights=info.weights, biases=info.biases, arc_tm=info.arc_tm, w_extra_constraints=we,
+                  b_extra_constraints=be, iso=0.0, flip_insideout=False)
+        cuam.AnalyticMarching(states=None, points=None, **kw)             # from the seeds stored on the device
+        d_stored, n_stored = cuam.digest(), cuam.stats()["n_faces"]
+        cuam.AnalyticMarching(states=st, points=pts, **kw)
+        assert cuam.digest()["raw"] == d_stored["raw"] and n_stored > 0
+        cuam.seed_dichotomy(info.weights, info.biases, info.arc_tm, we, be, 0.0, init_num=300, seed=6)
+        assert not np.array_equal(cuam.seeds()[0], pts)
+        if name == "chair":        # a closed surface: the region set does not depend on where the search starts
+            cuam.AnalyticMarching(states=None, points=None, **kw)
+            assert cuam.digest()["region_set"] == d_stored["region_set"] and cuam.stats()["n_faces"] == 248228
+            orc = oracle_lib.march(info, st, pts)
+            assert cuam.digest()["topology_sum"] == oracle_lib.topology_sum(oracle_lib.canonical_faces(orc), info.state_len)
+    cuam.Destroy()

@@ -87,6 +87,40 @@ def test_dichotomy_reproducible_and_on_surface():
     assert float(m(a).abs().mean()) < 1e-3
 
 
+def test_other_initialisers_find_the_surface():
+    """`sphere_tracing`, `gradient_descent` and `dichotomy(provided_surfpts=...)` (reference
+    backend/main.py:112-249, 263-264) with the reference's default argument dicts: points on the iso-surface
+    (mean |f - iso| below avg_eps), inside the ball, honouring extra constraints; gradient_descent returns exactly
+    init_num points."""
+    from analyticmesh_b200.initializers import gradient_descent, sphere_tracing
+    from analyticmesh_b200.main import GRADIENT_DESCENT_DICT, SPHERE_TRACING_DICT
+    from analyticmesh_b200.utils import get_boundary
+    m = zoo.sphere(width=64, depth=2)              # SDF-like: f ~ |x| - 0.5
+    for p in m.parameters():
+        p.requires_grad_(False)
+    w_e, b_e = get_boundary('cube', min_vert=(-1.0, -1.0, 0.0), max_vert=(1.0, 1.0, 1.0))     # upper half space
+    g = torch.Generator().manual_seed(3)
+    a = dict(SPHERE_TRACING_DICT['args'], init_num=256, w_extra_constraints=w_e, b_extra_constraints=b_e, generator=g)
+    pts = sphere_tracing(m, 0.0, **a)
+    assert 0 < pts.shape[0] <= 256 and pts.shape[1] == 3
+    assert float(m(pts).abs().mean()) < 2e-3 and float(pts[:, 2].min()) > 0.0 and float((pts ** 2).sum(1).max()) < 1.0
+    a = dict(GRADIENT_DESCENT_DICT['args'], init_num=128, w_extra_constraints=w_e, b_extra_constraints=b_e, generator=g)
+    pts = gradient_descent(m, 0.05, **a)
+    assert pts.shape == (128, 3)
+    assert float((m(pts) - 0.05).abs().mean()) < 5e-3 and float(pts[:, 2].min()) > 0.0
+    # dichotomy around provided surface points: the trial points are the given points + N(0, std)
+    seeds = dichotomy(m, 0.0, 64, generator=torch.Generator().manual_seed(1), rng=random.Random(1))
+    near = dichotomy(m, 0.0, 200, provided_surfpts=seeds, provided_surfstd=0.02,
+                     generator=torch.Generator().manual_seed(2), rng=random.Random(2))
+    assert near.shape == (200, 3) and float(m(near).abs().mean()) < 1e-3
+    d = torch.cdist(near, seeds).min(dim=1).values
+    assert float(d.max()) < 0.2                                # they stay in the neighbourhood of the given points
+    # a level set that lies outside the ball: every traced point is filtered out (the reference does the same)
+    far = sphere_tracing(m, 5.0, **dict(SPHERE_TRACING_DICT['args'], init_num=32, time_out=20, w_extra_constraints=None,
+                                        b_extra_constraints=None, generator=g))
+    assert far.shape[0] == 0
+
+
 def test_seed_fixtures_are_current():
     """the committed seeds are what make_seeds.py generates (guards against silent drift)"""
     for name in ("polytope", "chair_cube"):

@@ -115,6 +115,55 @@ def test_full_config4_sampled_against_oracle(oracle_lib):
     cuam.Destroy()
 
 
+def test_config5_latent_shapes_sampled_against_oracle(oracle_lib):
+    """BASELINE config 5 at full size: two of the latent-conditioned 8x512 shapes, marched back to back in ONE
+    environment (only biases[0] changes: exactly one tensor is re-staged), each checked like config 4 -- a sample of
+    its visited states recomputed by the oracle on that shape's network, edge incidence, Euler characteristic."""
+    import random
+    from analyticmesh_b200 import cuam, zoo
+    from analyticmesh_b200.netinfo import NetInfo
+    from analyticmesh_b200.initializers import dichotomy, states_of
+    model = zoo.by_name("mlp8x512s")
+    biases0 = zoo.latent_shapes(model, 64)
+    rs = np.random.RandomState(1)
+    first = True
+    seen = set()
+    for k in (0, 37):
+        with torch.no_grad():
+            model.linears[0].bias.copy_(biases0[k])
+        pts = dichotomy(model, 0.0, 1024, generator=torch.Generator().manual_seed(k), rng=random.Random(k))
+        info = NetInfo.from_model(model)
+        st = np.ascontiguousarray(states_of(model, pts).numpy())
+        if first:
+            cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table, num_extra_constraints=0)
+        cuam.AnalyticMarching(weights=info.weights, biases=info.biases, states=st, points=pts.double().numpy(),
+                              arc_tm=info.arc_tm, w_extra_constraints=np.zeros((0, 3)), b_extra_constraints=np.zeros(0),
+                              iso=0.0, flip_insideout=False)
+        s = cuam.stats()
+        assert s["n_faces"] == s["n_states"] > 10_000_000 and s["n_overflow"] == s["n_unbounded"] == 0, s
+        if not first:
+            assert s["n_tensors_reloaded"] == 1, s                   # the layer-1 table only
+        first = False
+        ids = np.unique(rs.randint(0, s["n_states"], 768))
+        g = cuam.gather_states(ids)
+        orc = oracle_lib.process_states(info, g["keys"], g["seedpt"][:, :3], np.where(g["parent"] < 0, -1, g["via"]))
+        of = oracle_lib.canonical_faces(orc)
+        L = info.state_len
+        for i, kb in enumerate(parity.key_bytes(g["keys"], L)):
+            n = int(g["counts"][i])
+            want = of[kb]
+            assert want is not None and tuple(int(e) for e in g["edges"][i, :n]) == want[0], (k, int(ids[i]))
+            assert np.abs(g["xyz"][i, :n] - want[1]).max() < 1e-9
+        inc = cuam.edge_incidence()
+        assert inc["boundary"] == inc["neighbour_missing"] == inc["neighbour_without_edge"] == 0, inc
+        cuam.CombineMesh(scale=1.0, center=[0.0, 0.0, 0.0])
+        s = cuam.stats()
+        assert s["n_vertices"] - inc["matched"] // 2 + s["n_faces"] == 2 and s["n_stitch_miss"] == 0
+        seen.add(cuam.digest()["region_set"])
+    assert len(seen) == 2                                            # the two shapes are different surfaces
+    cuam.Destroy()
+
+
 def _torchrun(n, script, *args, timeout=900):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, script), *args]
