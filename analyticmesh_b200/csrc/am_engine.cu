@@ -1281,6 +1281,7 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     const unsigned cgrid = (unsigned)((mine + CLIP_WARPS - 1) / CLIP_WARPS);
     switch (h->clip_minb) {   // AM_B200_CLIP_MINB: 2 = two CTAs/SM, no spills (default); 3 = three CTAs/SM
         case 3: launch_k(clip_kernel<3, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
+        case 4: launch_k(clip_kernel<2, 2, 3, true>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
         default: launch_k(clip_kernel<2, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
     }
     ++h->stats.n_launches;
@@ -1802,6 +1803,7 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         if (const char *e = getenv("AM_B200_INCREMENTAL")) h->incremental = atoi(e) != 0;
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
         CK(cudaFuncSetAttribute(clip_kernel<3, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
+        CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
         if (const char *e = getenv("AM_B200_CLIP_MINB")) h->clip_minb = atoi(e);
         h->counters.reserve(CNT_NUM * 8);
         {

@@ -91,7 +91,40 @@ __device__ __forceinline__ void clip_cp16(void *smem, const void *gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 
-template <int MINB, int RPL, int DEPTH>
+// ---- bulk (TMA 1-D) streaming: one instruction of one lane moves a whole 64-row block (2 KiB) and signals an
+// mbarrier; the inherited rows leave shared memory the same way (bulk shared -> global).  Replaces 4 predicated
+// 16-byte cp.async + 4 16-byte stores per lane and block.
+__device__ __forceinline__ void clip_mbar_init(uint32_t bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+}
+__device__ __forceinline__ void clip_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 24)) asm volatile("trap;\n");       // a lost copy must fail loudly, never hang the GPU
+    }
+}
+__device__ __forceinline__ void clip_bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint32_t bar)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void clip_bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    const unsigned src = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+
+template <int MINB, int RPL, int DEPTH, bool BULK = false>
 __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipArgs a)
 {
     pdl_enter();
@@ -101,6 +134,7 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
                                                      // slots k..k+3 repeat vertex 0 (unguarded 4-way loop)
     __shared__ int s_ed[CLIP_WARPS][VSLOTS];
     __shared__ uint32_t s_key[CLIP_WARPS][CLIP_KEY_WORDS];
+    __shared__ __align__(8) unsigned long long s_bar[BULK ? CLIP_WARPS : 1][DEPTH];   // one mbarrier per ring slot (BULK)
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int li = blockIdx.x * CLIP_WARPS + wib;
@@ -133,6 +167,15 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
     int k = 0;
     int n_inconsistent = 0;
     bool overflow = false;
+    const uint32_t bar0 = BULK ? (uint32_t)__cvta_generic_to_shared(&s_bar[BULK ? wib : 0][0]) : 0u;
+    uint32_t bar_phase = 0;                          // bit d: parity the next wait on ring slot d must see
+    if (BULK) {
+        if (lane == 0) {
+            for (int d = 0; d < DEPTH; ++d) clip_mbar_init(bar0 + 8u * d);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+    }
     for (int attempt = 0;; ++attempt) {
     k = 0;
     overflow = false;
@@ -190,6 +233,7 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
 
     // per-warp ring of DEPTH blocks of RPL * 32 rows: the next DEPTH-1 blocks are in flight without holding registers
     double *ring = s_ring + (size_t)wib * DEPTH * (RPL * 32) * 4;
+
     // applies the cutting planes of one 32-row half block, one at a time in row order (p, rs: this lane's row)
     auto apply_cuts = [&](unsigned long long todo, const double (&p)[RPL][4], const double (&rs)[RPL], int ebase) {
         while (todo) {
@@ -283,7 +327,21 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
         // a block is BR * 32 contiguous bytes: copy instruction i moves its 16-byte pieces 32 i .. 32 i + 31
         // (fully coalesced 512 B), whichever rows they belong to; the rows are read back after a warp sync
         const double *src = rows0 + (size_t)lane * 2;
+        int n_issued = 0, n_waited = 0;      // BULK: blocks whose copy was issued / whose barrier was consumed
         auto fetch = [&](int b) {            // rows BR b .. BR b + BR - 1 -> ring slot b % DEPTH
+            if (BULK) {
+                if (b < nblk) {
+                    if (lane == 0) {
+                        if (wr != nullptr)   // the slot's previous block may still be read by its bulk store
+                            asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+                        const int rows = (nrows - b * BR < BR) ? (nrows - b * BR) : BR;
+                        clip_bulk_load(ring + (size_t)(b % DEPTH) * (BR * 4), rows0 + (size_t)b * (BR * 4),
+                                       (uint32_t)rows * 32u, bar0 + 8u * (uint32_t)(b % DEPTH));
+                    }
+                    ++n_issued;
+                }
+                return;
+            }
             double *dst = ring + (size_t)(b % DEPTH) * (BR * 4) + lane * 2;
             const double *r = src + (size_t)b * (BR * 4);
             const int row0 = b * BR + (lane >> 1);
@@ -292,19 +350,37 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
                 if (row0 + 16 * i < nrows) clip_cp16(dst + i * 64, r + i * 64);
             asm volatile("cp.async.commit_group;\n" ::);
         };
+        auto wait_block = [&](int b) {       // block b has landed in its ring slot
+            if (BULK) {
+                const uint32_t d = (uint32_t)(b % DEPTH);
+                clip_mbar_wait(bar0 + 8u * d, (bar_phase >> d) & 1u);
+                bar_phase ^= 1u << d;
+                ++n_waited;
+            } else {
+                asm volatile("cp.async.wait_group %0;\n" ::"n"(DEPTH - 2));
+            }
+            __syncwarp();                    // every lane is past its reads of the slot that is refilled next
+        };
 #pragma unroll
         for (int b = 0; b < DEPTH - 1; ++b) fetch(b);
         for (int b = 0; b < nblk && k > 0 && !overflow; ++b) {
-            asm volatile("cp.async.wait_group %0;\n" ::"n"(DEPTH - 2));
-            __syncwarp();                            // the pieces of this lane's rows were copied by other lanes
+            wait_block(b);
             if (wr != nullptr) {                     // inherited rows: materialise them in the own buffer
-                const double *slot = ring + (size_t)(b % DEPTH) * (BR * 4) + lane * 2;
-                double *dst = wr + (size_t)b * (BR * 4);
-                const int row0 = b * BR + (lane >> 1);
+                if (BULK) {
+                    if (lane == 0) {
+                        const int rows = (nrows - b * BR < BR) ? (nrows - b * BR) : BR;
+                        clip_bulk_store(a.P_own + (size_t)s * a.p_stride + (size_t)b * (BR * 4),
+                                        ring + (size_t)(b % DEPTH) * (BR * 4), (uint32_t)rows * 32u);
+                    }
+                } else {
+                    const double *slot = ring + (size_t)(b % DEPTH) * (BR * 4) + lane * 2;
+                    double *dst = wr + (size_t)b * (BR * 4);
+                    const int row0 = b * BR + (lane >> 1);
 #pragma unroll
-                for (int i = 0; i < 2 * RPL; ++i)
-                    if (row0 + 16 * i < nrows)
-                        *reinterpret_cast<double2 *>(dst + i * 64) = *reinterpret_cast<const double2 *>(slot + i * 64);
+                    for (int i = 0; i < 2 * RPL; ++i)
+                        if (row0 + 16 * i < nrows)
+                            *reinterpret_cast<double2 *>(dst + i * 64) = *reinterpret_cast<const double2 *>(slot + i * 64);
+                }
             }
             const double *mine = ring + (size_t)(b % DEPTH) * (BR * 4) + lane * 4;
             double2 lo[RPL], hi[RPL];
@@ -363,7 +439,12 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
             for (int h = 0; h < RPL; ++h) todo |= (unsigned long long)__ballot_sync(FULL, cuts[h]) << (32 * h);
             if (todo) apply_cuts(todo, p, rs, c0 + b * BR);
         }
-        asm volatile("cp.async.wait_all;\n" ::);   // drain before the next segment reuses the ring
+        if (BULK) {                                 // drain: every issued copy is consumed before the ring is reused
+            while (n_waited < n_issued) wait_block(n_waited);
+            if (wr != nullptr && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_all;\n" ::);   // drain before the next segment reuses the ring
+        }
         __syncwarp();
     }
 

@@ -1,8 +1,12 @@
 // split.cuh -- the affine-composition GEMM on the 5th-generation tensor cores (tcgen05, kind::i8).
+// Bounded error, NOT bit-identical to the reference's FMA chain: tests/test_split_gpu.py checks the rows against
+// the integer restatement (bit for bit) AND against the oracle's FP64 rows (within the bound stated below).
 //
 // tcgen05 has no FP64 kind, so the FP64 contraction  P_out = W . diag(mask) . P_in  (compose.cuh) is
-// computed by an error-free integer split ("Ozaki scheme"): every row of W and every column of the
-// masked P_in is scaled by a power of two and cut into SD signed base-256 digits,
+// computed by a fixed-point integer split ("Ozaki scheme") whose only errors are the truncation of the operands
+// and the dropped low-order digit products -- every product that IS formed and every accumulation is exact:
+// every row of W and every column of the masked P_in is scaled by a power of two and cut into SD signed
+// base-256 digits,
 //
 //        x  =  2^(e-6) * sum_t d_t 2^(-8t) + r,   d_t in [-128, 127],  |r| <= 2^(e - 8 SD + 1),  2^e > max |x|
 //

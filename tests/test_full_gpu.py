@@ -212,3 +212,21 @@ def test_bench_digest_is_the_same_at_every_gpu_count():
         outs.append(json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]))
     assert outs[0]["digest"]["ordered"] == outs[1]["digest"]["ordered"], (outs[0]["digest"], outs[1]["digest"])
     assert outs[0]["config"]["faces_per_step_rank0"] == outs[1]["config"]["faces_per_step_rank0"]
+
+
+def test_clip_bulk_copy_variant_is_bit_identical():
+    """The clip kernel's TMA 1-D streaming variant (cp.async.bulk + mbarrier ring, bulk shared->global store of the
+    inherited rows; AM_B200_CLIP_MINB=4) gives the same mesh bit for bit as the cp.async ring, on a DMMA-path network,
+    a tcgen05-path network with read-through, and a case with extra constraints.  Subprocesses: a trapping kernel must
+    not take the test session down."""
+    import json
+    cases = ["chair", "mlp3x256s_cube", "chair_cube", "mlp8x512s_cube"]
+    digests = []
+    for variant in ("2", "4"):
+        env = dict(os.environ, AM_B200_CLIP_MINB=variant)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_check.py"), *cases], capture_output=True,
+                           text=True, timeout=600, cwd=ROOT, env=env)
+        assert r.returncode == 0, (variant, r.stdout[-2000:], r.stderr[-3000:])
+        digests.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    for c in cases:
+        assert digests[0][c]["raw"] == digests[1][c]["raw"] and digests[0][c]["faces"] > 0, (c, digests)

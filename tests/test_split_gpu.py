@@ -49,6 +49,13 @@ def test_planes_equal_integer_restatement(name, sd, monkeypatch, oracle_lib):
     # the level plane is the FMA chain over these rows: close to the oracle's
     p, e = oracle_lib.compose(case["info"], st[0], iso=0.125)
     assert np.allclose(equ[0], e, rtol=0, atol=1e-11 * max(1.0, np.abs(e).max()))
+    # ... and the rows themselves stay within the split's error bound of the oracle's FP64 FMA chain: operands are
+    # truncated 8 SD - 2 bits below their row / column maximum and the digit products with i + j >= SD are dropped
+    # (1.0e-15 / 5.7e-16 / 2.3e-13 of the layer's largest entry for SD = 7 / 8 / 6, compounded over depth)
+    bound = {6: 5e-12, 7: 5e-14, 8: 5e-14}[sd]
+    for i in range(min(4, st.shape[0])):
+        p, _ = oracle_lib.compose(case["info"], st[i], iso=0.125)
+        assert np.abs(planes[i] - p).max() <= bound * max(1.0, np.abs(p).max()), (name, sd, i, np.abs(planes[i] - p).max())
 
 
 @pytest.mark.parametrize("name", ["skipnet", "chair", "mlp4x128s", "mlp3x256s_cube"])
