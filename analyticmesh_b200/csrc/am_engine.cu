@@ -427,6 +427,7 @@ struct am_handle {
     int last_n_chain = 1;
     long long pdl_below = 4096;                 // states per rank and level below which launches use PDL
     bool force_perm_order = false;
+    bool equ_warp = true;                       // AM_B200_EQU_WARP=0: the sequential level-plane kernel on every path
     int n_chains = 0;   // 0 = automatic: 1 on a single GPU (launches fill the machine), 4 when sharded (measured +1.4 % at 8 GPUs)
     cudaStream_t chain_stream[MAX_CHAINS] = {};
     cudaEvent_t fork_event = nullptr, join_event[MAX_CHAINS] = {};
@@ -889,7 +890,10 @@ struct am_handle {
             }
             const int mine = chain_slots(Sc, c, nc);
             if (mine <= 0) return;
-            launch_k(equ_kernel, dim3((mine * 4 + 127) / 128), dim3(128), 0, cs, e);
+            if (gemm_variant == 2 && e.n_skips == 0 && equ_warp)      // warp per state, coalesced rows (compose.cuh)
+                launch_k(equ_warp_kernel, dim3((mine + 7) / 8), dim3(256), 0, cs, e);
+            else
+                launch_k(equ_kernel, dim3((mine * 4 + 127) / 128), dim3(128), 0, cs, e);
             ++stats.n_launches;
             CK(cudaGetLastError());
         };
@@ -1282,6 +1286,8 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     switch (h->clip_minb) {   // AM_B200_CLIP_MINB: 2 = two CTAs/SM, no spills (default); 3 = three CTAs/SM
         case 3: launch_k(clip_kernel<3, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
         case 4: launch_k(clip_kernel<2, 2, 3, true>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
+        case 5: launch_k(clip_kernel<2, 2, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 4), st, ca); break;
+        case 6: launch_k(clip_kernel<2, 2, 5>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 5), st, ca); break;
         default: launch_k(clip_kernel<2, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
     }
     ++h->stats.n_launches;
@@ -1797,6 +1803,7 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         h->bal_cuts.reserve((XCHG_MAX_WORLD + 1) * 4);
         if (const char *e = getenv("AM_B200_BALANCE")) h->balance = atoi(e) != 0;
         if (const char *e = getenv("AM_B200_PERM_ORDER")) h->force_perm_order = atoi(e) != 0;
+        if (const char *e = getenv("AM_B200_EQU_WARP")) h->equ_warp = atoi(e) != 0;
         if (const char *e = getenv("AM_B200_TRACE_EVERY")) h->trace_every = std::max(1, atoi(e));
         if (const char *e = getenv("AM_B200_PDL_BELOW")) h->pdl_below = atoll(e);
         h->xcursor.reserve(64);
@@ -1804,6 +1811,8 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
         CK(cudaFuncSetAttribute(clip_kernel<3, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
+        CK(cudaFuncSetAttribute(clip_kernel<2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 4)));
+        CK(cudaFuncSetAttribute(clip_kernel<2, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 5)));
         if (const char *e = getenv("AM_B200_CLIP_MINB")) h->clip_minb = atoi(e);
         h->counters.reserve(CNT_NUM * 8);
         {

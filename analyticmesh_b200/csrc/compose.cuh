@@ -448,4 +448,41 @@ __global__ void equ_kernel(const EquArgs a)
     a.equ[(size_t)s * 4 + c] = v;
 }
 
+// Warp-cooperative level plane (tcgen05 path, no skip into the output layer): one warp per state, lane l owns the
+// neurons k = l, l + 32, ... (coalesced 1 KiB row reads instead of 512 dependent FMAs per thread), partial sums are
+// combined by a fixed butterfly, so the result is deterministic (it differs from the sequential chain of equ_kernel
+// in the last bits only; the DMMA path keeps equ_kernel, whose chain is the oracle's bit for bit).
+__global__ void __launch_bounds__(256) equ_warp_kernel(const EquArgs a)
+{
+    pdl_enter();
+    const int lane = threadIdx.x & 31;
+    const int li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int pos = chain_position(li, a.tile, a.tile_stride, a.tile_offset);
+    if (pos >= a.S) return;
+    const int s = a.idx ? a.idx[pos] : pos;
+    const uint32_t *key = a.keys + (size_t)s * a.kw;
+    const double *rows = a.in + (size_t)s * a.in_stride;
+    if (a.bucket != nullptr && a.bucket[s] == a.D) rows = a.alt_in + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.in_stride;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = lane; k < a.K; k += 32) {
+        const int bit = a.bit0 + k;
+        if ((key[bit >> 5] >> (bit & 31)) & 1u) {
+            const double w = a.w[k];
+            const double2 p = *reinterpret_cast<const double2 *>(rows + (size_t)k * 4);
+            const double2 q = *reinterpret_cast<const double2 *>(rows + (size_t)k * 4 + 2);
+            acc[0] = fma(w, p.x, acc[0]); acc[1] = fma(w, p.y, acc[1]);
+            acc[2] = fma(w, q.x, acc[2]); acc[3] = fma(w, q.y, acc[3]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] += __shfl_xor_sync(0xFFFFFFFFu, acc[c], o);
+    if (lane < 4) {
+        double v = (lane == 0) ? acc[0] : (lane == 1) ? acc[1] : (lane == 2) ? acc[2] : acc[3];
+        if (lane == 3) v = v + a.bias - a.iso;
+        a.equ[(size_t)s * 4 + lane] = v;
+    }
+}
+
 }  // namespace amb

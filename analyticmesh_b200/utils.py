@@ -13,10 +13,18 @@ def get_boundary(boundary_type='cube', **kwargs):
     return w, b
 
 
-def estimate_am_time(model):
-    """The reference's fitted wall-time model for ITS engine (reference backend/utils.py:76-90);
-    kept for API compatibility -- it does not describe this engine."""
-    a, b, c, d, e, f = 1.94452188, 0.13816182, -0.14536181, 0.59338494, -1.20459825, 1.17841059
+def estimate_am_time(model, reference_engine=False):
+    """Estimated am_time (seconds) of `model`: the reference's model  t(l, n) = (a n)^(b l + c) * n^d * l^e * f  for
+    l hidden layers of mean width n (reference backend/utils.py:76-90), with the six constants RE-FITTED to this
+    engine on one B200 (tools/fit_am_time.py: 21 SAL geometric-init MLPs, depth 2..8, width 64..512, 1024 seeds,
+    float64; profiles/r02_fit_am_time.json; largest relative error of the fit 38%).
+    reference_engine=True returns the reference's own fit for ITS engine (measured on the cube-clipped 8x512
+    workloads: 63-106x slower than this engine, profiles/r02_bench_reference_cuda.json)."""
+    if reference_engine:
+        a, b, c, d, e, f = 1.94452188, 0.13816182, -0.14536181, 0.59338494, -1.20459825, 1.17841059
+    else:
+        a, b, c, d, e, f = (0.017110196732240516, 0.1228606661815844, 0.3233928770244429, 1.0322686311872493,
+                            1.4752353570366534, 8.491691646153003e-06)
     nodes = model.nodes
     layers = len(nodes) - 2
     width = sum(nodes[1:-1]) / layers
