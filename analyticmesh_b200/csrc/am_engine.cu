@@ -415,7 +415,9 @@ struct am_handle {
     long long lazy_lb = 0, lazy_prev_lb = 0;
     const double *fused_add_in = nullptr;       // input skip of the layer being launched, applied in the GEMM epilogue
     int fused_add_identity = 0;
-    int clip_minb = 2;                          // clip kernel variant (AM_B200_CLIP_MINB): 2 CTAs/SM, no spills; 3 = 3 CTAs/SM
+    // clip kernel variant (AM_B200_CLIP_MINB): 5 = 2 CTAs/SM, ring of 4 blocks per warp (default, measured best:
+    // profiles/r02_bench_clip_depth.md); 2 = ring of 3; 6 = ring of 5; 3 = 3 CTAs/SM (spills); 4 = TMA 1-D bulk copies
+    int clip_minb = 5;
     int num_sms = 148;
     std::vector<SplitWeights> splitW, splitTM;  // index h = 1..D-1 / transform index
     DevBuf bdig, bscale;                        // plane digits [SD][b_ncap][b_pitch] and column scales of the current launch
@@ -427,6 +429,7 @@ struct am_handle {
     int last_n_chain = 1;
     long long pdl_below = 4096;                 // states per rank and level below which launches use PDL
     bool force_perm_order = false;
+    int finalize_G = 8;
     bool equ_warp = true;                       // AM_B200_EQU_WARP=0: the sequential level-plane kernel on every path
     int n_chains = 0;   // 0 = automatic: 1 on a single GPU (launches fill the machine), 4 when sharded (measured +1.4 % at 8 GPUs)
     cudaStream_t chain_stream[MAX_CHAINS] = {};
@@ -1286,9 +1289,9 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     switch (h->clip_minb) {   // AM_B200_CLIP_MINB: 2 = two CTAs/SM, no spills (default); 3 = three CTAs/SM
         case 3: launch_k(clip_kernel<3, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
         case 4: launch_k(clip_kernel<2, 2, 3, true>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
-        case 5: launch_k(clip_kernel<2, 2, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 4), st, ca); break;
         case 6: launch_k(clip_kernel<2, 2, 5>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 5), st, ca); break;
-        default: launch_k(clip_kernel<2, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
+        case 2: launch_k(clip_kernel<2, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
+        default: launch_k(clip_kernel<2, 2, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 4), st, ca); break;
     }
     ++h->stats.n_launches;
     CK(cudaGetLastError());
@@ -1654,7 +1657,15 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         a.n_states = (int)h->n_states;
         a.cap_states = (int)std::min<size_t>(h->cap_states, (size_t)0x7FFFFFFF);
         if (timing) tk = h->span_begin();
-        h->dispatch_group([&](auto g) { launch_k(finalize_kernel<decltype(g)::value>, dim3(gb), dim3(256), 0, st, a); });
+        // the winners' keys are copied by the group: one uint4 per lane and 128 key bits (a parent without winners
+        // leaves at once, so the wider group costs nothing there)
+        const int Gf = h->finalize_G;
+        const unsigned gbf = (unsigned)((S * Gf + 255) / 256);
+        switch (Gf) {
+            case 32: launch_k(finalize_kernel<32>, dim3(gbf), dim3(256), 0, st, a); break;
+            case 16: launch_k(finalize_kernel<16>, dim3(gbf), dim3(256), 0, st, a); break;
+            default: h->dispatch_group([&](auto g) { launch_k(finalize_kernel<decltype(g)::value>, dim3(gb), dim3(256), 0, st, a); });
+        }
         if (timing) h->span_end(tk, 11);
         ++h->stats.n_launches;
         CK(cudaGetLastError());
@@ -1804,6 +1815,12 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         if (const char *e = getenv("AM_B200_BALANCE")) h->balance = atoi(e) != 0;
         if (const char *e = getenv("AM_B200_PERM_ORDER")) h->force_perm_order = atoi(e) != 0;
         if (const char *e = getenv("AM_B200_EQU_WARP")) h->equ_warp = atoi(e) != 0;
+        h->finalize_G = std::min(32, std::max(h->G, pow2_group(h->kw4)));          // one lane per 128 key bits
+        if (const char *e = getenv("AM_B200_FINALIZE_G")) {
+            const int g = atoi(e);
+            if (g == 8 || g == 16 || g == 32) h->finalize_G = g;
+        }
+        if (h->finalize_G != 32 && h->finalize_G != 16) h->finalize_G = h->G;
         if (const char *e = getenv("AM_B200_TRACE_EVERY")) h->trace_every = std::max(1, atoi(e));
         if (const char *e = getenv("AM_B200_PDL_BELOW")) h->pdl_below = atoll(e);
         h->xcursor.reserve(64);

@@ -83,7 +83,16 @@ def roofline(variant, split_digits, achieved, fp64_peak, launches, ms, flops):
     except Exception:
         pass
     peak = 2.0 * bf16 / products
-    return {"bound": "tensor", "kernel": "split_gemm_kernel", "achieved": achieved, "peak": peak,
+    instr = None
+    try:      # the instruction's own ceiling, measured with tools/int8_peak.cu on a B200 of this pool (register-free MMA loop)
+        ip = json.load(open(os.path.join(ROOT, "profiles", "r02_int8_peak.json")))
+        instr = {"int8_tops_instruction_peak": ip["split_mix_tops"],
+                 "frac_of_instruction_peak": achieved * products / ip["split_mix_tops"],
+                 "source": "profiles/r02_int8_peak.json: tcgen05.mma kind::i8 issued back to back on resident shared-memory "
+                           "operands (the 10 instructions per K step of this kernel), short burst, no power cap"}
+    except Exception:
+        pass
+    return {"bound": "tensor", "kernel": "split_gemm_kernel", "achieved": achieved, "peak": peak, "instruction_peak": instr,
             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic("split_gemm_kernel", flops / max(launches, 1)),
             "traffic_source": "scaled from the committed ncu --set full capture (profiles/ncu_traffic.json), not measured in this run",
             "launches": launches, "avg_launch_ms": avg_ms,
@@ -168,8 +177,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "CPU restatement of the reference algorithm "
-                   "(oracle/am_oracle.c, OpenMP); the reference itself has no CPU path"},
+        "config": base_config(args),
+        "details": {"note": "CPU restatement of the reference algorithm (oracle/am_oracle.c, OpenMP); the reference itself "
+                            "has no CPU path; every step is a bounded SAMPLE of the march"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -378,6 +388,13 @@ def run_batch(args, n_shapes):
         dist.destroy_process_group()
 
 
+def base_config(args):
+    """The part of `config` that names the workload: identical in this engine's line and in the reference arm's."""
+    return {"workload": workload_name(args),
+            "l2_note": "every step streams >= 9 GB of keys and >100 GB of plane rows through a 126 MB L2; inputs are far "
+                       "larger than L2, no flush needed"}
+
+
 def workload_name(args):
     d, w = args.workload[3:].rstrip("s").split("x")
     return (f"{args.workload}: SAL geometric-init ReLU MLP 3-[{w}]x{d}-1" +
@@ -572,10 +589,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "faces_per_step_rank0": last["n_faces"],
+            "config": base_config(args),
+            "details": {"faces_per_step_rank0": last["n_faces"],
                        "states_per_step_rank0": last["n_states"], "bfs_levels": last["n_levels"],
-                       "l2_note": "every step streams >= 9 GB of keys and >100 GB of plane rows through a 126 MB L2; "
-                                  "inputs are far larger than L2, no flush needed",
                        "parallelism": (f"1 process per GPU; compose+clip sharded by state owner over {world} GPUs, visited set "
                                        "sharded by key hash; per BFS level the polygons and winner masks are pushed into the "
                                        "peers' inboxes over NVLink by the engine's kernels (CUDA IPC peer memory, device-side "

@@ -219,7 +219,7 @@ def test_bench_digest_is_the_same_at_every_gpu_count():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
         outs.append(json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]))
     assert outs[0]["digest"]["ordered"] == outs[1]["digest"]["ordered"], (outs[0]["digest"], outs[1]["digest"])
-    assert outs[0]["config"]["faces_per_step_rank0"] == outs[1]["config"]["faces_per_step_rank0"]
+    assert outs[0]["details"]["faces_per_step_rank0"] == outs[1]["details"]["faces_per_step_rank0"]
 
 
 def test_clip_bulk_copy_variant_is_bit_identical():
