@@ -1290,6 +1290,9 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
         case 3: launch_k(clip_kernel<3, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
         case 4: launch_k(clip_kernel<2, 2, 3, true>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
         case 6: launch_k(clip_kernel<2, 2, 5>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 5), st, ca); break;
+        case 7: launch_k(clip_kernel<3, 1, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(1, 4), st, ca); break;
+        case 8: launch_k(clip_kernel<4, 1, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(1, 4), st, ca); break;
+        case 9: launch_k(clip_kernel<3, 1, 6>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(1, 6), st, ca); break;
         case 2: launch_k(clip_kernel<2, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
         default: launch_k(clip_kernel<2, 2, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 4), st, ca); break;
     }
@@ -1830,6 +1833,9 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 3)));
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 4)));
         CK(cudaFuncSetAttribute(clip_kernel<2, 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(2, 5)));
+        CK(cudaFuncSetAttribute(clip_kernel<3, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(1, 4)));
+        CK(cudaFuncSetAttribute(clip_kernel<4, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(1, 4)));
+        CK(cudaFuncSetAttribute(clip_kernel<3, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_ring_bytes(1, 6)));
         if (const char *e = getenv("AM_B200_CLIP_MINB")) h->clip_minb = atoi(e);
         h->counters.reserve(CNT_NUM * 8);
         {
