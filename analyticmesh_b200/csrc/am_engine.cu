@@ -23,6 +23,8 @@
 
 #include <cuda.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "../../include/am_b200.h"
 #include "clip.cuh"
@@ -415,9 +417,11 @@ struct am_handle {
     long long lazy_lb = 0, lazy_prev_lb = 0;
     const double *fused_add_in = nullptr;       // input skip of the layer being launched, applied in the GEMM epilogue
     int fused_add_identity = 0;
-    // clip kernel variant (AM_B200_CLIP_MINB): 5 = 2 CTAs/SM, ring of 4 blocks per warp (default, measured best:
-    // profiles/r02_bench_clip_depth.md); 2 = ring of 3; 6 = ring of 5; 3 = 3 CTAs/SM (spills); 4 = TMA 1-D bulk copies
-    int clip_minb = 5;
+    // clip kernel variant (AM_B200_CLIP_MINB), measured in profiles/r02_bench_clip_depth.md: 7 (default) = 3 CTAs/SM, one
+    // row per lane, ring of 4 blocks per warp (24 instead of 16 resident warps: the kernel is occupancy / latency bound);
+    // 9 = same with a ring of 6; 5 / 2 / 6 = 2 CTAs/SM, two rows per lane, ring of 4 / 3 / 5; 3 = 3 CTAs/SM two rows
+    // (spills); 8 = 4 CTAs/SM (spills); 4 = TMA 1-D bulk copies
+    int clip_minb = 7;
     int num_sms = 148;
     std::vector<SplitWeights> splitW, splitTM;  // index h = 1..D-1 / transform index
     DevBuf bdig, bscale;                        // plane digits [SD][b_ncap][b_pitch] and column scales of the current launch
@@ -430,6 +434,7 @@ struct am_handle {
     long long pdl_below = 4096;                 // states per rank and level below which launches use PDL
     bool force_perm_order = false;
     int finalize_G = 8;
+    bool push_in_clip = true;                   // AM_B200_PUSH_IN_CLIP=0: separate xchg_pack_kernel
     bool equ_warp = true;                       // AM_B200_EQU_WARP=0: the sequential level-plane kernel on every path
     int n_chains = 0;   // 0 = automatic: 1 on a single GPU (launches fill the machine), 4 when sharded (measured +1.4 % at 8 GPUs)
     cudaStream_t chain_stream[MAX_CHAINS] = {};
@@ -1285,16 +1290,26 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
     ca.counters = h->counters.as<unsigned long long>();
     ca.tile_stride = n_chain; ca.tile_offset = chain; ca.tile = h->chain_tile();
+    ca.push_on = 0;
+    if (h->p2p && h->shard_world > 1 && h->push_in_clip) {      // the clip warp pushes its polygon to every rank itself
+        ca.push_on = 1;
+        for (int q = 0; q < h->shard_world; ++q) ca.push.base[q] = h->xpeers.base[q];
+        ca.push.world = h->shard_world; ca.push.rank = h->shard_rank;
+        ca.push.region_off = h->xlay.region(h->shard_rank) + h->xlay.edge_off();
+        ca.push.xyz_off = h->xlay.xyz_off() - h->xlay.edge_off();
+        ca.push.cnt_base = h->xlay.cnt_base; ca.push.where_base = h->xlay.where_base;
+        ca.push.cap_corners = h->xlay.cap_corners; ca.push.cursor = h->xcursor.as<int>();
+    }
     const unsigned cgrid = (unsigned)((mine + CLIP_WARPS - 1) / CLIP_WARPS);
     switch (h->clip_minb) {   // AM_B200_CLIP_MINB: 2 = two CTAs/SM, no spills (default); 3 = three CTAs/SM
         case 3: launch_k(clip_kernel<3, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
         case 4: launch_k(clip_kernel<2, 2, 3, true>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
         case 6: launch_k(clip_kernel<2, 2, 5>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 5), st, ca); break;
-        case 7: launch_k(clip_kernel<3, 1, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(1, 4), st, ca); break;
         case 8: launch_k(clip_kernel<4, 1, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(1, 4), st, ca); break;
         case 9: launch_k(clip_kernel<3, 1, 6>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(1, 6), st, ca); break;
         case 2: launch_k(clip_kernel<2, 2, 3>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 3), st, ca); break;
-        default: launch_k(clip_kernel<2, 2, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 4), st, ca); break;
+        case 5: launch_k(clip_kernel<2, 2, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(2, 4), st, ca); break;
+        default: launch_k(clip_kernel<3, 1, 4>, dim3(cgrid), dim3(CLIP_WARPS * 32), clip_ring_bytes(1, 4), st, ca); break;
     }
     ++h->stats.n_launches;
     CK(cudaGetLastError());
@@ -1387,7 +1402,7 @@ void store_faces_p2p(am_handle *h, long long sid0, int Sc, Scratch sc, const int
     h->f_off.reserve((size_t)Sc * 4, 0, false);
     const bool tm = h->timing_on();
     size_t e0 = 0;
-    if (n_mine > 0) {
+    if (n_mine > 0 && !h->push_in_clip) {
         XchgPackArgs pa{};      // the cursor is zero: cleared by the previous level's winner kernel
         pa.idx = idx; pa.n = n_mine; pa.cnt = sc.cnt; pa.edges = sc.edges; pa.verts = sc.verts;
         pa.cursor = h->xcursor.as<int>(); pa.p = h->xpeers; pa.lay = h->xlay; pa.counters = cnt;
@@ -1818,6 +1833,7 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         if (const char *e = getenv("AM_B200_BALANCE")) h->balance = atoi(e) != 0;
         if (const char *e = getenv("AM_B200_PERM_ORDER")) h->force_perm_order = atoi(e) != 0;
         if (const char *e = getenv("AM_B200_EQU_WARP")) h->equ_warp = atoi(e) != 0;
+        if (const char *e = getenv("AM_B200_PUSH_IN_CLIP")) h->push_in_clip = atoi(e) != 0;
         h->finalize_G = std::min(32, std::max(h->G, pow2_group(h->kw4)));          // one lane per 128 key bits
         if (const char *e = getenv("AM_B200_FINALIZE_G")) {
             const int g = atoi(e);
@@ -2272,7 +2288,9 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         {
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
-            double gib = 64.0;
+            // the sharded march cannot fall back to chunked recomputation and indexes the level buffers by level-local
+            // state (only 1/world of the rows is ever written): give it more of the 180 GB
+            double gib = 96.0;        // capped by half of the free memory below
             if (const char *e = getenv("AM_B200_RESIDENT_GIB")) gib = atof(e);
             const size_t have = free_b + h->lvl_planes[0].cap + h->lvl_planes[1].cap;
             h->resident_budget = std::min<size_t>((size_t)(gib * (1ull << 30)), have / 2);
@@ -2472,17 +2490,29 @@ int am_export(am_handle *h, const char *path, int is_polymesh, int is_float32)
             }
         }
     });
-    FILE *f = fopen(path, "wb");
-    if (!f) {
+    // the T threads write disjoint slices of the file with pwrite: the copy into the page cache, which a single
+    // fwrite serialises (0.1 s for the 512 MB mesh of the 8x512 network), runs in parallel as well
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) {
         h->err = std::string("am_export: cannot open ") + path;
         return AM_ERR_IO;
     }
-    const size_t wr = fwrite(buf.get(), 1, total, f);
-    fclose(f);
-    if (wr != total) {
-        h->err = std::string("am_export: short write to ") + path;
-        return AM_ERR_IO;
-    }
+    std::vector<int> bad(T, 0);
+    run_threads([&](int t) {
+        size_t off = total * (size_t)t / (size_t)T;
+        const size_t end = total * (size_t)(t + 1) / (size_t)T;
+        while (off < end) {
+            const ssize_t w = pwrite(fd, buf.get() + off, end - off, (off_t)off);
+            if (w <= 0) { bad[t] = 1; break; }
+            off += (size_t)w;
+        }
+    });
+    const int rc_close = close(fd);
+    for (int t = 0; t < T; ++t)
+        if (bad[t] || rc_close != 0) {
+            h->err = std::string("am_export: short write to ") + path;
+            return AM_ERR_IO;
+        }
     return AM_OK;
 }
 

@@ -61,6 +61,8 @@ struct ClipArgs {
     double *out_verts;        // [S][VSLOTS][3]
     unsigned long long *counters;
     int tile_stride, tile_offset, tile;   // chained launches (compose.cuh chain_position); stride <= 1: the whole list
+    int push_on;              // sharded march: the polygon goes straight into every rank's exchange block (xchg.cuh) ...
+    PeerPush push;            // ... instead of the local scratch (out_cnt / out_edges / out_verts are then unused)
 };
 
 __device__ __forceinline__ double det3(double a, double b, double c, double d, double e, double f, double g, double h,
@@ -471,7 +473,27 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
         if (overflow) atomicAdd(a.counters + CNT_OVERFLOW, 1ull);
         if (n_inconsistent) atomicAdd(a.counters + CNT_INCONSISTENT, (unsigned long long)n_inconsistent);
         if (keep && k > VERT_MAX_REF) atomicAdd(a.counters + CNT_OVER_VERTMAX, 1ull);
-        a.out_cnt[s] = keep ? k : 0;
+        if (!a.push_on) a.out_cnt[s] = keep ? k : 0;
+    }
+    int push_off = 0, kk = keep ? k : 0;
+    if (a.push_on) {
+        // the owner's push (was a separate pack kernel): compact slot from this rank's cursor, then size + location
+        // into EVERY rank's block -- also for a state without polygon, whose entry would otherwise be stale
+        if (lane == 0 && kk > 0) {
+            push_off = atomicAdd(a.push.cursor, kk);
+            if (push_off + kk > a.push.cap_corners) {
+                atomicAdd(a.counters + CNT_XCHG_ERROR, 1ull << 32);
+                push_off = -1;
+            }
+        }
+        push_off = __shfl_sync(FULL, push_off, 0);
+        if (push_off < 0) { kk = 0; push_off = 0; }
+        if (lane < a.push.world) {
+            unsigned char *b = a.push.base[lane];
+            reinterpret_cast<int *>(b + a.push.cnt_base)[s] = kk;
+            reinterpret_cast<int2 *>(b + a.push.where_base)[s] = make_int2(a.push.rank, push_off);
+        }
+        if (kk == 0) return;
     }
     if (!keep) return;
     // g_i = edge carrying v_i -> v_{i+1} = ed[(i+1) % k]; reversed loop: v'_i = v_{k-1-i}, g'_i = ed[k-1-i]
@@ -491,9 +513,19 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
     // output slot of this lane after rotation by besti
     if (lane < k) {
         const int dst = (lane - besti + k) % k;
-        a.out_edges[(size_t)s * VSLOTS + dst] = g;
-        double *ov = a.out_verts + ((size_t)s * VSLOTS + dst) * 3;
-        ov[0] = vx[vsrc][0]; ov[1] = vx[vsrc][1]; ov[2] = vx[vsrc][2];
+        if (a.push_on) {
+            const double x = vx[vsrc][0], y = vx[vsrc][1], z = vx[vsrc][2];
+            for (int q = 0; q < a.push.world; ++q) {
+                unsigned char *r = a.push.base[q] + a.push.region_off;
+                reinterpret_cast<int *>(r)[push_off + dst] = g;
+                double *ov = reinterpret_cast<double *>(r + a.push.xyz_off) + (size_t)(push_off + dst) * 3;
+                ov[0] = x; ov[1] = y; ov[2] = z;
+            }
+        } else {
+            a.out_edges[(size_t)s * VSLOTS + dst] = g;
+            double *ov = a.out_verts + ((size_t)s * VSLOTS + dst) * 3;
+            ov[0] = vx[vsrc][0]; ov[1] = vx[vsrc][1]; ov[2] = vx[vsrc][2];
+        }
     }
 }
 

@@ -75,6 +75,20 @@ __device__ __forceinline__ void pdl_enter()
     pdl_wait();
 }
 
+// Sharded march: where a polygon goes when its owner pushes it into every rank's exchange block (xchg.cuh); the
+// clip kernel does the push itself, so the layout is a plain struct here.
+constexpr int PEER_MAX = 16;
+struct PeerPush {
+    unsigned char *base[PEER_MAX];   // exchange block of every rank as mapped in this process
+    int world, rank;
+    unsigned long long region_off;   // this rank's polygon region inside a block: edges [cap_corners] ...
+    unsigned long long xyz_off;      // ... | vertices [cap_corners][3], relative to region_off
+    unsigned long long cnt_base;     // [level states] int: polygon size, written by the state's owner
+    unsigned long long where_base;   // [level states] int2: (source rank, corner offset)
+    int cap_corners;
+    int *cursor;                     // device counter of this rank: corners pushed so far in the level
+};
+
 // first activation bit of every hidden layer (kernel parameter)
 constexpr int MAX_LAYERS = 64;
 struct LayerOffs {
