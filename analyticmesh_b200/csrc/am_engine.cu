@@ -434,6 +434,12 @@ struct am_handle {
     long long pdl_below = 4096;                 // states per rank and level below which launches use PDL
     bool force_perm_order = false;
     int finalize_G = 8;
+    // sharded march: the level buffers hold the owned states' rows only, at their permutation slot (AM_B200_COMPACT_ROWS)
+    bool compact_rows = true, prev_compact = false;
+    DevBuf slot_of[2];                          // inverse permutation of the previous / current level
+    int slot_buf = 0;
+    int cur_rows_by_slot = 0;                   // set while a level is processed
+    const int *cur_slot_of = nullptr, *cur_prev_slot_of = nullptr;
     bool push_in_clip = true;                   // AM_B200_PUSH_IN_CLIP=0: separate xchg_pack_kernel
     bool equ_warp = true;                       // AM_B200_EQU_WARP=0: the sequential level-plane kernel on every path
     int n_chains = 0;   // 0 = automatic: 1 on a single GPU (launches fill the machine), 4 when sharded (measured +1.4 % at 8 GPUs)
@@ -533,7 +539,7 @@ struct am_handle {
                          &digest_acc, &xcursor, &wmask,
                          &level_cursor, &fs_sums, &fs_off, &fs_sums2, &fs_off2, &fs_ticket, &bal_loads, &bal_cuts,
                          &sd_pts, &sd_valid, &sd_val, &sd_flags, &sd_offs, &sd_lists, &sd_pos, &sd_neg, &sd_mid, &sd_err, &sd_tot,
-                         &sd_keys};
+                         &sd_keys, &slot_of[0], &slot_of[1]};
         for (auto &b : Wrow) b.release();
         for (auto &b : Brow) b.release();
         for (auto &b : sd_act) b.release();
@@ -711,6 +717,7 @@ struct am_handle {
         sa.tile_stride = n_chain; sa.tile_offset = chain;
         sa.alt_from_slot = alt_from_slot; sa.alt_src = alt_src; sa.parent = parent.as<int>();
         sa.lb = (int)lazy_lb; sa.prev_lb = (int)lazy_prev_lb;
+        sa.rows_by_slot = cur_rows_by_slot; sa.prev_slot_of = cur_prev_slot_of;
         const bool t = timing_on() && n_chain == 1;      // per-kernel events (the roofline of the dominant kernel)
         size_t e0 = 0;
         if (t) e0 = span_begin();
@@ -730,6 +737,7 @@ struct am_handle {
         g.add_in = accumulate ? nullptr : fused_add_in;
         g.add_identity = accumulate ? 0 : fused_add_identity;
         g.n_tiles = g.m_tiles * mine;
+        g.rows_by_slot = cur_rows_by_slot;
         if (t) e0 = span_begin();
         launch_k(split_gemm_kernel<SD>, dim3((unsigned)std::min(g.n_tiles, num_sms)), dim3(SP_THREADS), SplitCfg<SD>::SMEM, cs, 
             w.map, b_map(w.Kpad), g);
@@ -750,6 +758,7 @@ struct am_handle {
         g.bias = bias_; g.S = Sc; g.accumulate = accumulate;
         g.perm = perm_; g.m_tiles = Mpad_ / GM_BM;
         g.tile_stride = n_chain; g.tile_offset = chain;
+        g.rows_by_slot = cur_rows_by_slot;
         cudaStream_t cs = (n_chain > 1) ? chain_stream[chain] : stream;
         bool launched = false;
         auto go = [&](auto cfg) {
@@ -842,7 +851,8 @@ struct am_handle {
                     if (sk.src == 0) {
                         const long long tot = (long long)Sc * M;
                         skip_input_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, cs>>>(
-                            out, 4LL * R, M, Sc, identity ? nullptr : TM[sk.tm].as<double>(), prm, tile_states, n_chain, c);
+                            out, 4LL * R, M, Sc, identity ? nullptr : TM[sk.tm].as<double>(), prm, tile_states, n_chain, c,
+                            cur_rows_by_slot);
                         ++stats.n_launches;
                     } else {
                         long long sstride;
@@ -850,7 +860,8 @@ struct am_handle {
                         if (identity) {
                             const long long tot = (long long)Sc * M * 4;
                             skip_hidden_identity_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, cs>>>(
-                                out, 4LL * R, src, sstride, keys0, kw, off[sk.src], M, Sc, prm, tile_states, n_chain, c);
+                                out, 4LL * R, src, sstride, keys0, kw, off[sk.src], M, Sc, prm, tile_states, n_chain, c,
+                                cur_rows_by_slot);
                             ++stats.n_launches;
                         } else {
                             launch_gemm(TMt[sk.tm].as<double>(), tm_Mpad[sk.tm], M, n[sk.src], src, sstride, off[sk.src],
@@ -875,6 +886,7 @@ struct am_handle {
             e.equ = equ.as<double>();
             e.bucket = nullptr;
             e.tile_stride = nc; e.tile_offset = c; e.tile = chain_tile();
+            e.rows_by_slot = cur_rows_by_slot; e.prev_slot_of = cur_prev_slot_of;
             if (lazy_prev != nullptr && D >= 2) {
                 e.bucket = bucket.as<int>(); e.parent = parent.as<int>();
                 e.lb = (int)lazy_lb; e.prev_lb = (int)lazy_prev_lb; e.D = D;
@@ -1290,6 +1302,7 @@ void run_clip(am_handle *h, long long sid0, int n, const double *planes_base, in
     ca.out_cnt = sc.cnt; ca.out_edges = sc.edges; ca.out_verts = sc.verts;
     ca.counters = h->counters.as<unsigned long long>();
     ca.tile_stride = n_chain; ca.tile_offset = chain; ca.tile = h->chain_tile();
+    ca.rows_by_slot = h->cur_rows_by_slot; ca.prev_slot_of = h->cur_prev_slot_of;
     ca.push_on = 0;
     if (h->p2p && h->shard_world > 1 && h->push_in_clip) {      // the clip warp pushes its polygon to every rank itself
         ca.push_on = 1;
@@ -1443,15 +1456,34 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
 
     // Incremental mode: this level's plane rows stay resident (ping-pong with the previous level) so
     // that children copy the rows of the layers before their flipped neuron instead of recomputing.
+    // Sharded march: a rank only ever writes the rows of the states it owns, so the level buffer holds just those, at
+    // their position in the bucket-sorted permutation ("compact rows"); the parent's rows are found through the
+    // previous level's inverse permutation.  The number of owned states is known on the host (bucket histogram).
+    const bool sharded = h->shard_world > 1;
+    long long n_owned = S;
+    if (sharded) {
+        if (lb == 0) {
+            n_owned = (S - h->shard_rank + h->shard_world - 1) / h->shard_world;
+        } else if (h->next_valid) {
+            n_owned = 0;
+            for (int b = 1; b <= h->D; ++b) n_owned += h->h_next[b];
+        }
+    }
+    const bool compact = sharded && h->compact_rows && (lb == 0 || h->next_valid);
+    const long long n_rows = compact ? std::max<long long>(n_owned, 1) : S;
     const bool resident = h->incremental && h->D >= 2 && S <= (1 << 26) &&
-                          2 * (size_t)S * per_state <= h->resident_budget;
+                          2 * (size_t)n_rows * per_state <= h->resident_budget;
     if (resident) {
         const int cur = h->prev_resident ? 1 - h->prev_buf : 0;
         DevBuf &pb = h->lvl_planes[cur];
-        pb.reserve((size_t)S * per_state, 0, true);
+        pb.reserve((size_t)n_rows * per_state, 0, true);
         double *base = pb.as<double>();
         h->ensure_chunk_scratch_no_planes((size_t)S);
-        const bool sharded = h->shard_world > 1;
+        h->slot_buf = 1 - h->slot_buf;
+        if (compact) h->slot_of[h->slot_buf].reserve((size_t)S * 4, 0, false);
+        h->cur_rows_by_slot = compact ? 1 : 0;
+        h->cur_slot_of = compact ? h->slot_of[h->slot_buf].as<int>() : nullptr;
+        h->cur_prev_slot_of = (h->prev_resident && h->prev_compact) ? h->slot_of[1 - h->slot_buf].as<int>() : nullptr;
         Scratch sc = scratch_of(h, (size_t)S);
         h->ensure_corners((size_t)(corners_upper + S * VSLOTS), (size_t)corners_upper);
         const uint32_t *keys0 = h->keys.as<uint32_t>() + (size_t)lb * h->kw;
@@ -1496,9 +1528,11 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
                                                         h->prev_resident ? (int)h->prev_lb : 0,
                                                         h->prev_resident ? (int)h->prev_S : 0, lo, bb, h->bucket.as<int>(),
                                                         h->level_cursor.as<int>(), h->perm.as<int>(),
-                                                        sharded ? h->owner.as<uint8_t>() : nullptr, h->shard_rank);
+                                                        sharded ? h->owner.as<uint8_t>() : nullptr, h->shard_rank,
+                                                        const_cast<int *>(h->cur_slot_of));
             ++h->stats.n_launches;
         } else {
+            if (compact) throw CudaFail{"compact level buffers need the bucket sizes on the host"};
             CK(cudaMemsetAsync(counts, 0, (size_t)(D + 3) * 4, st));
             classify_kernel<<<sb, 256, 0, st>>>(h->via.as<int>(), h->parent.as<int>(), (int)lb, (int)S,
                                                 h->prev_resident ? (int)h->prev_lb : 0, h->prev_resident ? (int)h->prev_S : 0,
@@ -1521,7 +1555,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         } else if (h->prev_resident) {
             copy_parent_rows_kernel<<<(unsigned)((S + 7) / 8), 256, 0, st>>>(
                 h->bucket.as<int>(), h->parent.as<int>(), (int)lb, (int)S, (int)h->prev_lb,
-                h->lvl_planes[h->prev_buf].as<double>(), base, 4LL * h->R, lo, h->n1);
+                h->lvl_planes[h->prev_buf].as<double>(), base, 4LL * h->R, lo, h->n1, h->cur_slot_of, h->cur_prev_slot_of);
             ++h->stats.n_launches;
             CK(cudaGetLastError());
         }
@@ -1554,6 +1588,9 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
         h->lazy_prev = nullptr;
         if (timing) h->span_end(t0, 2);
         h->prev_resident = true;
+        h->prev_compact = compact;
+        h->cur_rows_by_slot = 0;
+        h->cur_slot_of = h->cur_prev_slot_of = nullptr;
         h->prev_buf = cur;
         h->prev_lb = lb;
         h->prev_S = S;
@@ -1834,6 +1871,7 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
         if (const char *e = getenv("AM_B200_PERM_ORDER")) h->force_perm_order = atoi(e) != 0;
         if (const char *e = getenv("AM_B200_EQU_WARP")) h->equ_warp = atoi(e) != 0;
         if (const char *e = getenv("AM_B200_PUSH_IN_CLIP")) h->push_in_clip = atoi(e) != 0;
+        if (const char *e = getenv("AM_B200_COMPACT_ROWS")) h->compact_rows = atoi(e) != 0;
         h->finalize_G = std::min(32, std::max(h->G, pow2_group(h->kw4)));          // one lane per 128 key bits
         if (const char *e = getenv("AM_B200_FINALIZE_G")) {
             const int g = atoi(e);

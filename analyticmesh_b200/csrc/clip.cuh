@@ -61,6 +61,8 @@ struct ClipArgs {
     double *out_verts;        // [S][VSLOTS][3]
     unsigned long long *counters;
     int tile_stride, tile_offset, tile;   // chained launches (compose.cuh chain_position); stride <= 1: the whole list
+    int rows_by_slot;         // sharded march: own rows live at the list position (= permutation slot) ...
+    const int *prev_slot_of;  // ... and the parent's rows at prev_slot_of[parent - prev_lb]
     int push_on;              // sharded march: the polygon goes straight into every rank's exchange block (xchg.cuh) ...
     PeerPush push;            // ... instead of the local scratch (out_cnt / out_edges / out_verts are then unused)
 };
@@ -312,17 +314,19 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
         const int bkt = a.bucket[s];
         if (bkt >= 2 && bkt <= a.lo.D) {
             inh = a.lo.off[bkt + 1] - a.n1;
-            inh_src = a.P_prev + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.p_stride;
+            const int pi = a.parent[a.lb + s] - a.prev_lb;
+            inh_src = a.P_prev + (size_t)(a.prev_slot_of ? a.prev_slot_of[pi] : pi) * a.p_stride;
         }
     }
 #pragma unroll 1
     for (int seg = 0; seg < 4; ++seg) {
-        const double *own = a.P + (size_t)s * a.p_stride;
+        const int row = a.rows_by_slot ? slot : s;
+        const double *own = a.P + (size_t)row * a.p_stride;
         const double *rows0 = (seg == 0) ? a.P1 : (seg == 1) ? inh_src : (seg == 2) ? own + (size_t)inh * 4 : a.extra;
         const int c0 = (seg == 0) ? 0 : (seg == 1) ? a.n1 : (seg == 2) ? a.n1 + inh : a.L;
         const int nrows = (seg == 0) ? a.n1 : (seg == 1) ? inh : (seg == 2) ? a.L - a.n1 - inh : a.E;
         const bool has_bits = seg < 3;
-        double *wr = (seg == 1) ? a.P_own + (size_t)s * a.p_stride + (size_t)lane * 2 : nullptr;
+        double *wr = (seg == 1) ? a.P_own + (size_t)row * a.p_stride + (size_t)lane * 2 : nullptr;
         if (nrows <= 0 || k <= 0 || overflow) continue;
         constexpr int BR = RPL * 32;                 // rows per block
         const int nblk = (nrows + BR - 1) / BR;
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(CLIP_WARPS * 32, MINB) clip_kernel(const ClipA
                 if (BULK) {
                     if (lane == 0) {
                         const int rows = (nrows - b * BR < BR) ? (nrows - b * BR) : BR;
-                        clip_bulk_store(a.P_own + (size_t)s * a.p_stride + (size_t)b * (BR * 4),
+                        clip_bulk_store(a.P_own + (size_t)row * a.p_stride + (size_t)b * (BR * 4),
                                         ring + (size_t)(b % DEPTH) * (BR * 4), (uint32_t)rows * 32u);
                     }
                 } else {

@@ -74,6 +74,7 @@ struct GemmArgs {
                                 // of their flipped neuron, see classify_kernel); nullptr = identity
     int m_tiles;                // Mpad / GM_BM; blockIdx.x = s_tile * m_tiles + m_tile
     int tile_stride, tile_offset;   // this launch handles state tiles tile_offset, tile_offset + tile_stride, ...
+    int rows_by_slot;               // sharded march: a state's rows live at its permutation slot, not at its level index
                                     // (independent chains of launches on several streams fill each other's tails)
 };
 
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) compose_gemm_kernel(const
 #pragma unroll
     for (int i = 0; i < C::CHUNKS_B; ++i) {
         const int slot = s0 + (tid + i * C::THREADS) / (2 * C::BK);
-        bbase[i] = (slot < S) ? (long long)(a.perm ? a.perm[slot] : slot) * a.b_stride : -1;
+        bbase[i] = (slot < S) ? (long long)((a.perm && !a.rows_by_slot) ? a.perm[slot] : slot) * a.b_stride : -1;
     }
     __syncthreads();                                 // smask visible
 
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) compose_gemm_kernel(const
     for (int j = 0; j < C::NJ; ++j) {
         const int slot = s0 + wn * (2 * C::NJ) + j * 2 + (fk >> 1);
         if (slot >= S) continue;
-        const int s = a.perm ? a.perm[slot] : slot;
+        const int s = (a.perm && !a.rows_by_slot) ? a.perm[slot] : slot;
         double *dst = a.out + (size_t)s * a.out_stride + comp0;
 #pragma unroll
         for (int i = 0; i < C::MI; ++i) {
@@ -236,13 +237,13 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) compose_gemm_kernel(const
 
 // from the raw input: P[s][m][0..2] += T[m][0..2]   (T == nullptr: += I3)   process.h:86-92,109-115
 __global__ void skip_input_kernel(double *out, long long out_stride, int M, int S, const double *T, const int *perm,
-                                  int tile_states, int tile_stride, int tile_offset)
+                                  int tile_states, int tile_stride, int tile_offset, int rows_by_slot)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= (long long)S * M) return;
     const int slot = int(t / M), m = int(t % M);
     if ((slot / tile_states) % tile_stride != tile_offset) return;    // another chain's tile
-    const int s = perm ? perm[slot] : slot;
+    const int s = (perm && !rows_by_slot) ? perm[slot] : slot;
     double *p = out + (size_t)s * out_stride + (size_t)m * 4;
     if (T != nullptr) {
         p[0] += T[3 * m + 0];
@@ -256,7 +257,7 @@ __global__ void skip_input_kernel(double *out, long long out_stride, int M, int 
 // identity skip from hidden layer `src`: out[s][m][:] += bit(s, src_bit0+m) * in[s][m][:]   process.h:93-105
 __global__ void skip_hidden_identity_kernel(double *out, long long out_stride, const double *in, long long in_stride,
                                             const uint32_t *keys, int kw, int src_bit0, int M, int S, const int *perm,
-                                            int tile_states, int tile_stride, int tile_offset)
+                                            int tile_states, int tile_stride, int tile_offset, int rows_by_slot)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= (long long)S * M * 4) return;
@@ -265,9 +266,10 @@ __global__ void skip_hidden_identity_kernel(double *out, long long out_stride, c
     const int slot = int(r / M), m = int(r % M);
     if ((slot / tile_states) % tile_stride != tile_offset) return;
     const int s = perm ? perm[slot] : slot;
+    const int row = rows_by_slot ? slot : s;
     const int bit = src_bit0 + m;
     if ((keys[(size_t)s * kw + (bit >> 5)] >> (bit & 31)) & 1u)
-        out[(size_t)s * out_stride + (size_t)m * 4 + c] += in[(size_t)s * in_stride + (size_t)m * 4 + c];
+        out[(size_t)row * out_stride + (size_t)m * 4 + c] += in[(size_t)row * in_stride + (size_t)m * 4 + c];
 }
 
 // ---- incremental composition ----------------------------------------------------------------------
@@ -321,7 +323,7 @@ __global__ void scatter_kernel(const int *bucket, int S, int *cursor, int *perm)
 struct BucketBase { int base[MAX_LAYERS + 2]; };
 __global__ void classify_scatter_kernel(const int *via_edge, const int *parent, int lb, int S, int prev_lb, int prev_S,
                                         LayerOffs lo, BucketBase bb, int *bucket, int *cursor, int *perm,
-                                        const uint8_t *owner, int rank)
+                                        const uint8_t *owner, int rank, int *slot_of)
 {
     pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -334,12 +336,15 @@ __global__ void classify_scatter_kernel(const int *via_edge, const int *parent, 
         while (b < lo.D && e >= lo.off[b + 1]) ++b;
     }
     bucket[s] = b;
-    perm[bb.base[b] + atomicAdd(cursor + b, 1)] = s;
+    const int pos = bb.base[b] + atomicAdd(cursor + b, 1);
+    perm[pos] = s;
+    if (slot_of != nullptr) slot_of[s] = pos;       // inverse permutation: where the state's rows live (sharded march)
 }
 
 // rows of hidden layers 2..b of the parent -> own rows; one warp per state
 __global__ void copy_parent_rows_kernel(const int *bucket, const int *parent, int lb, int S, int prev_lb,
-                                        const double *prev, double *cur, long long stride, LayerOffs lo, int n1)
+                                        const double *prev, double *cur, long long stride, LayerOffs lo, int n1,
+                                        const int *slot_of, const int *prev_slot_of)
 {
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -347,8 +352,9 @@ __global__ void copy_parent_rows_kernel(const int *bucket, const int *parent, in
     const int b = bucket[s];
     if (b < 2 || b > lo.D) return;
     const long long n16 = (long long)(lo.off[b + 1] - n1) * 2;      // 16-byte pieces to copy
-    const uint4 *src = reinterpret_cast<const uint4 *>(prev + (size_t)(parent[lb + s] - prev_lb) * stride);
-    uint4 *dst = reinterpret_cast<uint4 *>(cur + (size_t)s * stride);
+    const int pi = parent[lb + s] - prev_lb;
+    const uint4 *src = reinterpret_cast<const uint4 *>(prev + (size_t)(prev_slot_of ? prev_slot_of[pi] : pi) * stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(cur + (size_t)(slot_of ? slot_of[s] : s) * stride);
     long long i = lane;
     for (; i + 96 < n16; i += 128) {                              // 4 independent 16 B loads in flight per lane
         const uint4 v0 = src[i], v1 = src[i + 32], v2 = src[i + 64], v3 = src[i + 96];
@@ -386,6 +392,9 @@ struct EquArgs {
     const double *alt_in;     // rows of the last hidden layer of the previous level's state 0
     // chained launches: this launch handles the list positions of tiles tile_offset, tile_offset + tile_stride, ...
     int tile_stride, tile_offset, tile;
+    // sharded march: own rows live at the list position (= permutation slot), the parent's at prev_slot_of[parent]
+    int rows_by_slot;
+    const int *prev_slot_of;
 };
 
 // i-th position handled by a chained launch -> position in the whole list (tiles of `tile` positions dealt round-robin)
@@ -428,8 +437,12 @@ __global__ void equ_kernel(const EquArgs a)
     if (pos >= a.S) return;
     const int s = a.idx ? a.idx[pos] : pos, c = t & 3;
     const uint32_t *key = a.keys + (size_t)s * a.kw;
-    const double *rows = a.in + (size_t)s * a.in_stride;
-    if (a.bucket != nullptr && a.bucket[s] == a.D) rows = a.alt_in + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.in_stride;
+    const int row = a.rows_by_slot ? pos : s;
+    const double *rows = a.in + (size_t)row * a.in_stride;
+    if (a.bucket != nullptr && a.bucket[s] == a.D) {
+        const int pi = a.parent[a.lb + s] - a.prev_lb;
+        rows = a.alt_in + (size_t)(a.prev_slot_of ? a.prev_slot_of[pi] : pi) * a.in_stride;
+    }
     double v = masked_chain(a.w, rows, key, a.bit0, a.K, c);
     if (c == 3) v += a.bias;
     for (int i = 0; i < a.n_skips; ++i) {
@@ -439,9 +452,9 @@ __global__ void equ_kernel(const EquArgs a)
         } else if (sk.kind == 2) {
             if (c < 3) v += sk.T[c];
         } else if (sk.kind == 3) {
-            if ((key[sk.src_bit0 >> 5] >> (sk.src_bit0 & 31)) & 1u) v += sk.src[(size_t)s * sk.src_stride + c];
+            if ((key[sk.src_bit0 >> 5] >> (sk.src_bit0 & 31)) & 1u) v += sk.src[(size_t)row * sk.src_stride + c];
         } else if (sk.kind == 4) {
-            v += masked_chain(sk.T, sk.src + (size_t)s * sk.src_stride, key, sk.src_bit0, sk.src_n, c);
+            v += masked_chain(sk.T, sk.src + (size_t)row * sk.src_stride, key, sk.src_bit0, sk.src_n, c);
         }
     }
     if (c == 3) v -= a.iso;
@@ -461,8 +474,11 @@ __global__ void __launch_bounds__(256) equ_warp_kernel(const EquArgs a)
     if (pos >= a.S) return;
     const int s = a.idx ? a.idx[pos] : pos;
     const uint32_t *key = a.keys + (size_t)s * a.kw;
-    const double *rows = a.in + (size_t)s * a.in_stride;
-    if (a.bucket != nullptr && a.bucket[s] == a.D) rows = a.alt_in + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.in_stride;
+    const double *rows = a.in + (size_t)(a.rows_by_slot ? pos : s) * a.in_stride;
+    if (a.bucket != nullptr && a.bucket[s] == a.D) {
+        const int pi = a.parent[a.lb + s] - a.prev_lb;
+        rows = a.alt_in + (size_t)(a.prev_slot_of ? a.prev_slot_of[pi] : pi) * a.in_stride;
+    }
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int k = lane; k < a.K; k += 32) {
         const int bit = a.bit0 + k;

@@ -97,12 +97,18 @@ struct SliceArgs {
     const double *alt_src;          // rows of this layer of the previous level's state 0
     const int *parent;              // global state id of the parent, indexed by global state id
     int lb, prev_lb;                // first state id of this / the previous level
+    // sharded march: own rows live at the permutation slot, the parent's at prev_slot_of[parent]
+    int rows_by_slot;
+    const int *prev_slot_of;
 };
 
 __device__ __forceinline__ const double *slice_rows_of(const SliceArgs &a, int slot, int s)
 {
-    if (slot >= a.alt_from_slot) return a.alt_src + (size_t)(a.parent[a.lb + s] - a.prev_lb) * a.stride;
-    return a.src + (size_t)s * a.stride;
+    if (slot >= a.alt_from_slot) {
+        const int pi = a.parent[a.lb + s] - a.prev_lb;
+        return a.alt_src + (size_t)(a.prev_slot_of ? a.prev_slot_of[pi] : pi) * a.stride;
+    }
+    return a.src + (size_t)(a.rows_by_slot ? slot : s) * a.stride;
 }
 
 template <int SD>
@@ -363,6 +369,7 @@ struct SplitArgs {
     int tile_stride, tile_offset;
     const double *add_in;       // fused skip connection from the raw input: out[m][0..2] += add_in[3 m + 0..2]
     int add_identity;           //   ... or += I3 (identity skip: rows m < 3 get +1 on their own column)
+    int rows_by_slot;           // sharded march: the output rows of slot p live at row p (not at perm[p])
 };
 
 // exact int32 -> double on the FP64 pipe (LOP3 + DADD; I2F.F64 runs at a quarter of that rate)
@@ -476,7 +483,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int m0 = (t % a.m_tiles) * SP_BM;
             const int s0 = ((t / a.m_tiles) * a.tile_stride + a.tile_offset) * SP_BS;
             // tile constants -> shared memory, hidden behind the tile's MMAs
-            if (e < SP_BS) s_perm[buf * SP_BS + e] = (s0 + e < a.S) ? (a.perm ? a.perm[s0 + e] : s0 + e) : -1;
+            if (e < SP_BS) s_perm[buf * SP_BS + e] = (s0 + e < a.S) ? ((a.perm && !a.rows_by_slot) ? a.perm[s0 + e] : s0 + e) : -1;
             if (e < SP_BN) s_scale[buf * SP_BN + e] = (s0 + (e >> 2) < a.S) ? a.scaleB[(size_t)s0 * 4 + e] : 0.0;
             const int m = m0 + q * 32 + lane;
             const bool m_ok = m < a.M;
