@@ -239,6 +239,18 @@ __global__ void finalize_kernel(const LevelArgs a)
             if ((e >> 7) == q) flip_bit(x, e & 127);
             dst[q] = x;
         }
+        // seed point of the child = mid-point of the shared edge; extent of the parent's polygon around it = a hint for
+        // the size of the child's polygon (clip.cuh starts from a square of a few times this size and retries if it was
+        // too small).  The corners are spread over the lanes (max is exact in any order).
+        const int j2 = (j + 1 == k) ? 0 : j + 1;
+        const double *p = a.face_xyz + (size_t)(fo + j) * 3, *q2 = a.face_xyz + (size_t)(fo + j2) * 3;
+        const double mx = 0.5 * (p[0] + q2[0]), my = 0.5 * (p[1] + q2[1]), mz = 0.5 * (p[2] + q2[2]);
+        double ext = 0.0;
+        for (int c = tile.thread_rank(); c < k; c += G) {
+            const double *v = a.face_xyz + (size_t)(fo + c) * 3;
+            ext = fmax(ext, fmax(fabs(v[0] - mx), fmax(fabs(v[1] - my), fabs(v[2] - mz))));
+        }
+        for (int o = G / 2; o > 0; o >>= 1) ext = fmax(ext, tile.shfl_xor(ext, o));
         if (tile.thread_rank() == 0) {
             a.hsum_w[nid] = hash_flip(a.hsum[sid], a.keys + (size_t)sid * a.kw, e);
             a.parent[nid] = sid;
@@ -250,16 +262,6 @@ __global__ void finalize_kernel(const LevelArgs a)
                     while (own + 1 < a.n_ranks && fidx >= a.cuts[own + 1]) ++own;
                 }
                 a.owner[nid] = uint8_t(own);
-            }
-            const int j2 = (j + 1 == k) ? 0 : j + 1;
-            const double *p = a.face_xyz + (size_t)(fo + j) * 3, *q2 = a.face_xyz + (size_t)(fo + j2) * 3;
-            const double mx = 0.5 * (p[0] + q2[0]), my = 0.5 * (p[1] + q2[1]), mz = 0.5 * (p[2] + q2[2]);
-            // extent of the parent's polygon around the shared edge: a hint for the size of the child's
-            // polygon (clip.cuh starts from a square of a few times this size and retries if it was too small)
-            double ext = 0.0;
-            for (int c = 0; c < k; ++c) {
-                const double *v = a.face_xyz + (size_t)(fo + c) * 3;
-                ext = fmax(ext, fmax(fabs(v[0] - mx), fmax(fabs(v[1] - my), fabs(v[2] - mz))));
             }
             a.seedpt[(size_t)nid * 4 + 0] = mx;
             a.seedpt[(size_t)nid * 4 + 1] = my;
