@@ -1513,7 +1513,7 @@ void process_level(am_handle *h, long long lb, long long le, double iso, int fli
             for (int b = 1; b <= h->D; ++b) n_owned += h->h_next[b];
         }
     }
-    const bool compact = sharded && h->compact_rows && (lb == 0 || h->next_valid);
+    const bool compact = sharded && h->p2p && h->compact_rows && (lb == 0 || h->next_valid);   // peer-memory mode only
     const long long n_rows = compact ? std::max<long long>(n_owned, 1) : S;
     const bool resident = h->incremental && h->D >= 2 && S <= (1 << 26) &&
                           2 * (size_t)n_rows * per_state <= h->resident_budget;

@@ -173,8 +173,7 @@ def test_weight_cache_with_device_tensors():
     assert cuam.stats()["n_tensors_reloaded"] == 0 and cuam.digest()["raw"] == d0
     B[1][3] += 1e-3                                        # one bias of the second layer, in place on the device
     cuam.AnalyticMarching(**kw)
-    assert cuam.stats()["n_tensors_reloaded"] == 0 or True   # biases are not counted as matrices ...
-    assert cuam.digest()["raw"] != d0                      # ... but the change must be seen
+    assert cuam.digest()["raw"] != d0                      # a changed bias is seen (biases are not counted as matrices)
     B[1][3] -= 1e-3
     W[2][0, 0] *= 1.0000001
     cuam.AnalyticMarching(**kw)
