@@ -345,6 +345,22 @@ def test_allreduce_union_world2_gloo():
     assert res == [(0, True), (1, True)]
 
 
+def test_native_host_selftest(tmp_path):
+    """The arithmetic helpers of the CUDA sources that run on the host as well (nvcc-compiled, executed on the CPU):
+    pairing bijection + Philox of the device initialiser, digit split of the tcgen05 path, exchange-block layout, hash
+    ownership and the chain deal of the sharded march (tests/native/host_selftest.cu)."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = str(tmp_path / "host_selftest")
+    src = os.path.join(ROOT, "tests", "native", "host_selftest.cu")
+    subprocess.run(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, src], check=True,
+                   capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "host selftest ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_seed_owner_rule():
     from analyticmesh_b200.parallel import owner_of_seeds
     assert owner_of_seeds(5, 2).tolist() == [0, 1, 0, 1, 0]
