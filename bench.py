@@ -1,6 +1,6 @@
 """bench.py -- faces/sec of one full Analytic Marching pass over the 8x512 SAL MLP (BASELINE.json config 4).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference|reference-cuda] [--workload batch64]
 
 One "step" = one complete march of the workload: seed states -> region BFS -> all polygons (the
 reference's `am_time` phase, backend/main.py:455-465).  Prints ONE JSON line on rank 0.
@@ -8,15 +8,24 @@ reference's `am_time` phase, backend/main.py:455-465).  Prints ONE JSON line on 
   value      faces/s, whole job, inputs (weights, seed states/points) already resident in HBM
   e2e        same metric through the C ABI with HOST buffers: host->device copies of weights and
              seeds and the device->host read of the stitched mesh (am_combine) inside the timed region
-  roofline   the dominant kernel (compose_gemm_kernel): its algorithmic flops / its CUDA-event time,
-             measured live on the engine's stream, against the FP64 DFMA peak measured in the same
-             process (am_fp64_peak_tflops; tools/fp64_peak.cu measured 37.0 TFLOP/s for DFMA and DMMA)
+  roofline   the dominant kernel -- split_gemm_kernel (tcgen05 kind::i8 split-integer composition GEMM) for layers
+             >= 256 wide, compose_gemm_kernel (FP64 DMMA) for narrower networks: its algorithmic flops
+             (2*M*K*4*S per launch) / its CUDA-event time measured live on the engine's stream, against
+             the int8 tensor peak derived from MEASURED_PEAKS.json divided by the number of digit products (and, beside
+             it, the instruction's own ceiling measured with tools/int8_peak.cu), or the FP64 DFMA/DMMA peak measured
+             in the same process (am_fp64_peak_tflops; tools/fp64_peak.cu: 37.0 TFLOP/s)
   cpu_baseline  the CPU oracle (oracle/am_oracle.c, OpenMP) on a bounded sample of the same workload
+  digest / mesh_check  device-side checksums of everything the march produced (numbering, keys, edge loops, every
+             coordinate bit) and edge incidence / Euler characteristic of the stitched mesh: the same values at every N
 
-N > 1: ONE march of the same network is spread over the N GPUs (am_set_shard): every rank composes and
-clips the states it owns, the per-level polygons are combined with one NCCL all-reduce, the frontier
-and visited set are replicated; value = faces of the mesh / max-over-ranks time ("strong").
---impl reference: the reference algorithm's CPU restatement on the host cores (rank 0 only).
+N > 1: ONE march of the same network is spread over the N GPUs (am_set_shard_p2p, csrc/xchg.cuh): every rank composes
+and clips the states it owns, the visited set is sharded by key hash, the level's polygons and winner masks are pushed
+into the peers' exchange blocks over NVLink by the engine's own kernels (CUDA-IPC peer memory, device-side barriers; no
+NCCL and no host synchronisation in the exchange); value = faces of the mesh / max-over-ranks time ("strong").
+AM_B200_SHARD=nccl selects the round-1 scheme (ncclAllReduce of the level's polygons) for comparison.
+--impl reference: the reference algorithm's CPU restatement on all host cores (rank 0 only), bounded sample per step.
+--impl reference-cuda: the reference's own CUDA build (baseline/_ref) and this engine on the same inputs, one process.
+--workload batch64: BASELINE config 5 (64 latent-conditioned shapes, replicas, shape k on GPU k mod N).
 """
 import argparse
 import json
