@@ -88,6 +88,14 @@ void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
     CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 
+template <typename F>
+void for_split_digits(F &&f)
+{
+    f(std::integral_constant<int, 6>{});
+    f(std::integral_constant<int, 7>{});
+    f(std::integral_constant<int, 8>{});
+}
+
 // ---- virtual-memory backed growth (CUDA VMM through the runtime's driver entry points: no libcuda link)
 struct VmApi {
     bool ok = false;
@@ -414,6 +422,8 @@ struct am_handle {
     // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
     int gemm_variant = 0;                       // 0/1: FP64 DMMA tiles, 2: tcgen05 int8 split (split.cuh)
     int split_digits = 7;
+    int split_epi = 1;            // epilogue warps per TMEM lane quarter of split_gemm_kernel (AM_B200_SPLIT_EPI = 1 | 2 | 4;
+                                  // 2 and 4 measured 3 % slower, profiles/r02_split_epilogue_warps.md)
     // read-through of the parent's rows instead of copy_parent_rows_kernel (tcgen05 path, no hidden-source skips)
     bool lazy_ok = false;
     const double *lazy_prev = nullptr;          // previous level's rows while a level is processed lazily, else nullptr
@@ -742,8 +752,12 @@ struct am_handle {
         g.n_tiles = g.m_tiles * mine;
         g.rows_by_slot = cur_rows_by_slot;
         if (t) e0 = span_begin();
-        launch_k(split_gemm_kernel<SD>, dim3((unsigned)std::min(g.n_tiles, num_sms)), dim3(SP_THREADS), SplitCfg<SD>::SMEM, cs, 
-            w.map, b_map(w.Kpad), g);
+        const dim3 ggrid((unsigned)std::min(g.n_tiles, num_sms));
+        switch (split_epi) {      // epilogue warps per TMEM lane quarter (split.cuh); results do not depend on it
+            case 2: launch_k(split_gemm_kernel<SD, 2, 16>, ggrid, dim3(split_threads(2)), SplitCfg<SD>::SMEM, cs, w.map, b_map(w.Kpad), g); break;
+            case 4: launch_k(split_gemm_kernel<SD, 4, 8>, ggrid, dim3(split_threads(4)), SplitCfg<SD>::SMEM, cs, w.map, b_map(w.Kpad), g); break;
+            default: launch_k(split_gemm_kernel<SD, 1, 16>, ggrid, dim3(split_threads(1)), SplitCfg<SD>::SMEM, cs, w.map, b_map(w.Kpad), g); break;
+        }
         if (t) span_end(e0, 4, 2.0 * M * (double)K * 4.0 * Sc);
         return true;
     }
@@ -1965,9 +1979,15 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
                 case 1: prep(GemmWide{}, compose_gemm_kernel<GemmWide>); break;
                 case 2:
                     if (kmax > 8192) throw CudaFail{"hidden layers wider than 8192 overflow the int32 digit accumulators"};
-                    CK(cudaFuncSetAttribute(split_gemm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitCfg<6>::SMEM));
-                    CK(cudaFuncSetAttribute(split_gemm_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitCfg<7>::SMEM));
-                    CK(cudaFuncSetAttribute(split_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SplitCfg<8>::SMEM));
+                    if (const char *e = getenv("AM_B200_SPLIT_EPI")) h->split_epi = atoi(e);
+                    if (h->split_epi != 2 && h->split_epi != 4) h->split_epi = 1;
+                    for_split_digits([&](auto sd) {
+                        constexpr int SD = decltype(sd)::value;
+                        const int bytes = (int)SplitCfg<SD>::SMEM;
+                        CK(cudaFuncSetAttribute(split_gemm_kernel<SD, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                        CK(cudaFuncSetAttribute(split_gemm_kernel<SD, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                        CK(cudaFuncSetAttribute(split_gemm_kernel<SD, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                    });
                     break;
                 default: prep(GemmDefault{}, compose_gemm_kernel<GemmDefault>); break;
             }

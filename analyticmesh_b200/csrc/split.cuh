@@ -22,15 +22,25 @@
 // i.e. the rounding of the result is at the level of an FP64 dot product; the dropped products
 // (i + j >= SD) are below 2^-50 of max|w| max|p| K.
 //
-// Kernel layout (persistent: one 192-thread CTA per SM strides over tiles of 128 output neurons x 16 states):
+// Kernel layout (persistent: one CTA of 64 + 128 EW threads per SM strides over tiles of 128 output neurons x 16 states):
 //   warp 0    TMA producer: per 32-byte K step one 3-D box of the weight digits [SD][128][32] and one of
 //             the plane digits [SD][64][32] (SWIZZLE_32B), multi-stage mbarrier ring; runs ahead into the
 //             next tile while the epilogue drains TMEM
 //   warp 1    TMEM allocation (512 columns, once) + single-thread MMA issue: for weight digit i ONE
 //             instruction covers the plane digits j = 0 .. SD-1-i, because their accumulators
 //             g = i + j are adjacent 64-column windows of TMEM (N = 64 (SD - i), cut at 256)
-//   warps 2-5 epilogue: tile constants staged in shared memory behind the MMAs, tcgen05.ld of the SD
-//             accumulators, exact int -> double, FP64 Horner, scale, bias, input-skip addend, 16-byte stores
+//   warps 2.. epilogue, EW warps per TMEM lane quarter (a warp may only read the lanes 32 (warp % 4) ..): tile constants
+//             staged in shared memory behind the MMAs, tcgen05.ld of the SD accumulators, exact int -> double, FP64
+//             Horner, scale, bias, input-skip addend, 16-byte stores.  One accumulator set fills TMEM (SD x 64 of the
+//             512 columns), so the next tile's MMAs wait until the LAST tcgen05.ld of the tile has completed: with
+//             EW = 1 that is after three of the four 16-column chunks have been loaded, converted and stored by the one
+//             warp of the quarter; with EW warps per quarter every warp drains only 64 / EW columns (in chunks of CW)
+//             and the serial part shrinks to (64 / EW - CW) columns of arithmetic.  Every output is computed by the
+//             same instruction sequence whatever EW: results are bit-identical (tools/epi_check.py).  MEASURED on the
+//             8x512 march (profiles/r02_split_epilogue_warps.md): EW = 2 and EW = 4 are 3 % SLOWER than EW = 1
+//             (1403 vs 1364 ms of GEMM time), i.e. the serial epilogue is not what keeps the tensor pipe at 58 %:
+//             the K loop itself is bound by the operand fill (43 008 B of TMA traffic per K step and SM against
+//             ~46 B/clk of TMA service per SM = 935 clk, the MMAs of a K step take 896-953 clk).  EW = 1 stays the default.
 // Plane digits come from slice_rows_reg_kernel (one pass, rows kept in registers) or slice_rows_kernel (any K).
 #pragma once
 #include <cuda.h>
@@ -43,7 +53,8 @@ constexpr int SP_BM = 128;        // output neurons per tile (TMEM lanes)
 constexpr int SP_BS = 16;         // states per tile
 constexpr int SP_BN = SP_BS * 4;  // columns per tile
 constexpr int SP_BK = 32;         // K bytes per pipeline stage = K of one kind::i8 instruction
-constexpr int SP_THREADS = 192;
+constexpr int SP_THREADS = 192;    // EW = 1; in general 64 + 128 EW (split_threads)
+__host__ __device__ constexpr int split_threads(int ew) { return 64 + 128 * ew; }
 constexpr int SP_KPAD = 32;       // digit rows are padded to a multiple of this many K bytes
 
 template <int SD>
@@ -353,6 +364,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16])
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_cols(uint32_t taddr, int (&v)[16]) { tc_ld16(taddr, v); }
+__device__ __forceinline__ void tc_ld_cols(uint32_t taddr, int (&v)[8]) { tc_ld8(taddr, v); }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 struct SplitArgs {
@@ -380,8 +399,9 @@ __device__ __forceinline__ double i32_to_f64(int x)
 
 // Persistent: gridDim.x CTAs (one per SM) stride over the tiles; the TMA producer runs ahead into the next
 // tile while the epilogue drains TMEM, TMEM / barriers are set up once per CTA.
-template <int SD>
-__global__ void __launch_bounds__(SP_THREADS, 1)
+// EW: epilogue warps per TMEM lane quarter (1, 2 or 4); CW: accumulator columns per tcgen05.ld chunk (16 or 8)
+template <int SD, int EW = 1, int CW = 16>
+__global__ void __launch_bounds__(split_threads(EW), 1)
 split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SplitArgs a)
 {
     using C = SplitCfg<SD>;
@@ -406,7 +426,7 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(bar_empty + 8 * i, 1);
         }
         mbar_init(bar_tfull, 1);
-        mbar_init(bar_tempty, 4);                                    // one arrive per epilogue warp
+        mbar_init(bar_tempty, 4 * EW);                               // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -473,9 +493,15 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else {
-        // ---- epilogue: this warp reads TMEM lanes [32 q, 32 q + 32), q = warp % 4 ------------------------
+        // ---- epilogue: this warp reads TMEM lanes [32 q, 32 q + 32), q = warp % 4, and of those the columns
+        // [part * COLS_W, (part + 1) * COLS_W) of every accumulator, CW at a time -------------------------------
+        static_assert(EW == 1 || EW == 2 || EW == 4, "epilogue warps per lane quarter");
+        static_assert((CW == 16 || CW == 8) && (SP_BN / EW) % CW == 0, "chunk width");
+        constexpr int COLS_W = SP_BN / EW;
+        constexpr int NCH = COLS_W / CW;
         const int q = warp & 3;
-        const int e = threadIdx.x - 64;                              // 0..127
+        const int part = (EW == 1) ? 0 : (warp - 2) >> 2;            // 0 .. EW-1
+        const int e = threadIdx.x - 64;                              // 0 .. 128 EW - 1
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t tphase = 0;
         int buf = 0;
@@ -493,26 +519,27 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (m_ok && a.add_in != nullptr) { add[0] = a.add_in[3 * m]; add[1] = a.add_in[3 * m + 1]; add[2] = a.add_in[3 * m + 2]; }
             if (m_ok && a.add_identity && m < 3) add[m] = 1.0;
             const bool has_add = a.add_in != nullptr || a.add_identity;
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            asm volatile("bar.sync 1, %0;\n" ::"n"(128 * EW) : "memory");
             mbar_wait(bar_tfull, tphase);
             tphase ^= 1u;
             tc_fence_after();
 #pragma unroll 1
-            for (int cb = 0; cb < SP_BN / 16; ++cb) {
-                int v[SD][16];
+            for (int cb = 0; cb < NCH; ++cb) {
+                const int c0 = part * COLS_W + cb * CW;              // first accumulator column of the chunk
+                int v[SD][CW];
 #pragma unroll
-                for (int g = 0; g < SD; ++g) tc_ld16(trow + (uint32_t)(g * SP_BN + cb * 16), v[g]);
+                for (int g = 0; g < SD; ++g) tc_ld_cols(trow + (uint32_t)(g * SP_BN + c0), v[g]);
                 tc_ld_wait();
-                if (cb == SP_BN / 16 - 1) {                          // TMEM fully read: the next tile's MMAs may start
-                    tc_fence_before();
+                if (cb == NCH - 1) {                                 // this warp's share of TMEM is read: the next tile's
+                    tc_fence_before();                               // MMAs start when every epilogue warp has arrived
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_tempty) : "memory");
                 }
 #pragma unroll
-                for (int st = 0; st < 4; ++st) {
-                    const int s = s_perm[buf * SP_BS + cb * 4 + st];
+                for (int st = 0; st < CW / 4; ++st) {
+                    const int s = s_perm[buf * SP_BS + (c0 >> 2) + st];
                     if (s < 0 || !m_ok) continue;
-                    const double *sb = s_scale + buf * SP_BN + cb * 16 + st * 4;
+                    const double *sb = s_scale + buf * SP_BN + c0 + st * 4;
                     double r[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
