@@ -640,7 +640,8 @@ def main():
         except Exception:
             pass
         if world == 1 and not args.no_cpu_baseline:
-            f, s, n = cpu_reference_sample(info, points, states, args.ref_states, threads=os.cpu_count() or 1)
+            # ~10 s of CPU work on a 16-core box (4 x the per-step sample of the reference arm)
+            f, s, n = cpu_reference_sample(info, points, states, 4 * args.ref_states, threads=os.cpu_count() or 1)
             out["cpu_baseline"] = {"value": f / s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"first {n} states of the same march (same network, same seeds), "
                                              f"{s:.1f} s of OpenMP CPU work"}
