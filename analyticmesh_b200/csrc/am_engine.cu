@@ -312,17 +312,17 @@ struct TmaApi {
 };
 
 // 3-D map over int8 digit planes [SD][rows][pitch]: box = 32 K bytes x box_rows rows x SD planes, SWIZZLE_32B
-CUtensorMap make_digit_map(const void *ptr, int k_bytes, size_t pitch, size_t rows, int sd, int box_rows)
+CUtensorMap make_digit_map(const void *ptr, int k_bytes, size_t pitch, size_t rows, int sd, int box_rows, int bk = SP_BK)
 {
     TmaApi &api = TmaApi::get();
     if (!api.encode) throw CudaFail{"cuTensorMapEncodeTiled is not available in this driver"};
     CUtensorMap m;
     const cuuint64_t dims[3] = {(cuuint64_t)k_bytes, (cuuint64_t)rows, (cuuint64_t)sd};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * rows};
-    const cuuint32_t box[3] = {(cuuint32_t)SP_BK, (cuuint32_t)box_rows, (cuuint32_t)sd};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, (cuuint32_t)sd};      // rows of bk bytes, swizzled in bk-byte spans
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult rc = api.encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(ptr), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) throw CudaFail{"cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")"};
     return m;
@@ -422,6 +422,8 @@ struct am_handle {
     // torch.distributed), frontier / visited set / mesh are replicated and stay bit-identical on all ranks
     int gemm_variant = 0;                       // 0/1: FP64 DMMA tiles, 2: tcgen05 int8 split (split.cuh)
     int split_digits = 7;
+    int split_bk = 64;            // K bytes per pipeline stage of split_gemm_kernel (AM_B200_SPLIT_BK = 32 | 64): 64-byte TMA rows
+                                  // fill shared memory faster than 32-byte rows, GEMM time -9.8 % (profiles/r02_split_bk64.md)
     int split_epi = 1;            // epilogue warps per TMEM lane quarter of split_gemm_kernel (AM_B200_SPLIT_EPI = 1 | 2 | 4;
                                   // 2 and 4 measured 3 % slower, profiles/r02_split_epilogue_warps.md)
     // read-through of the parent's rows instead of copy_parent_rows_kernel (tcgen05 path, no hidden-source skips)
@@ -699,13 +701,14 @@ struct am_handle {
         }
         for (auto &kv : b_maps)
             if (kv.first == kbytes) return kv.second;
-        b_maps.emplace_back(kbytes, make_digit_map(bdig.p, kbytes, b_pitch, b_ncap, split_digits, SP_BN));
+        b_maps.emplace_back(kbytes, make_digit_map(bdig.p, kbytes, b_pitch, b_ncap, split_digits, SP_BN, split_bk));
         return b_maps.back().second;
     }
     void ensure_split_scratch(size_t slots)
     {
-        size_t pitch = SP_KPAD;
-        for (int l = 1; l <= D; ++l) pitch = std::max<size_t>(pitch, (size_t)(n[l] + SP_KPAD - 1) / SP_KPAD * SP_KPAD);
+        const size_t unit = (size_t)std::max(SP_KPAD, split_bk);      // K is padded to whole pipeline stages
+        size_t pitch = unit;
+        for (int l = 1; l <= D; ++l) pitch = std::max<size_t>(pitch, ((size_t)n[l] + unit - 1) / unit * unit);
         size_t ncap = (std::max<size_t>(slots, SP_BS) * 4 + SP_BN - 1) / SP_BN * SP_BN;
         if (ncap <= b_ncap && pitch == b_pitch) return;
         ncap = std::max(ncap, (b_ncap + b_ncap / 2 + SP_BN - 1) / SP_BN * SP_BN);
@@ -744,7 +747,7 @@ struct am_handle {
         ++stats.n_launches;
         if (t) span_end(e0, 5, 0.0);
         SplitArgs g{};
-        g.k_steps = w.Kpad / SP_BK; g.M = M; g.m_tiles = w.Mpad / SP_BM; g.S = Sc; g.perm = perm_;
+        g.k_steps = (w.Kpad + split_bk - 1) / split_bk; g.M = M; g.m_tiles = w.Mpad / SP_BM; g.S = Sc; g.perm = perm_;
         g.out = out; g.out_stride = 4LL * R; g.bias = bias_; g.scaleA = w.scale.as<double>();
         g.scaleB = bscale.as<double>(); g.accumulate = accumulate; g.tile_stride = n_chain; g.tile_offset = chain;
         g.add_in = accumulate ? nullptr : fused_add_in;
@@ -753,7 +756,9 @@ struct am_handle {
         g.rows_by_slot = cur_rows_by_slot;
         if (t) e0 = span_begin();
         const dim3 ggrid((unsigned)std::min(g.n_tiles, num_sms));
-        switch (split_epi) {      // epilogue warps per TMEM lane quarter (split.cuh); results do not depend on it
+        if (split_bk == 64)       // 64-byte K slabs per stage (two MMA K steps, SWIZZLE_64B boxes); same results
+            launch_k(split_gemm_kernel<SD, 1, 16, 64>, ggrid, dim3(split_threads(1)), SplitCfg<SD, 64>::SMEM, cs, w.map, b_map(w.Kpad), g);
+        else switch (split_epi) { // epilogue warps per TMEM lane quarter (split.cuh); results do not depend on it
             case 2: launch_k(split_gemm_kernel<SD, 2, 16>, ggrid, dim3(split_threads(2)), SplitCfg<SD>::SMEM, cs, w.map, b_map(w.Kpad), g); break;
             case 4: launch_k(split_gemm_kernel<SD, 4, 8>, ggrid, dim3(split_threads(4)), SplitCfg<SD>::SMEM, cs, w.map, b_map(w.Kpad), g); break;
             default: launch_k(split_gemm_kernel<SD, 1, 16>, ggrid, dim3(split_threads(1)), SplitCfg<SD>::SMEM, cs, w.map, b_map(w.Kpad), g); break;
@@ -1065,7 +1070,8 @@ void upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st)
 
 void prepare_split_weights(am_handle *h, SplitWeights &sw, const double *w, int M, int K)
 {
-    sw.Kpad = (K + SP_KPAD - 1) / SP_KPAD * SP_KPAD;
+    const int unit = std::max(SP_KPAD, h->split_bk);      // K is padded to whole pipeline stages
+    sw.Kpad = (K + unit - 1) / unit * unit;
     sw.Mpad = (M + SP_BM - 1) / SP_BM * SP_BM;
     std::vector<signed char> dig;
     std::vector<double> scale;
@@ -1073,7 +1079,7 @@ void prepare_split_weights(am_handle *h, SplitWeights &sw, const double *w, int 
     upload(sw.dig, dig.data(), dig.size(), h->stream);
     upload(sw.scale, scale.data(), scale.size() * 8, h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    sw.map = make_digit_map(sw.dig.p, sw.Kpad, (size_t)sw.Kpad, (size_t)sw.Mpad, h->split_digits, SP_BM);
+    sw.map = make_digit_map(sw.dig.p, sw.Kpad, (size_t)sw.Kpad, (size_t)sw.Mpad, h->split_digits, SP_BM, h->split_bk);
     sw.ready = true;
 }
 
@@ -1981,12 +1987,15 @@ int am_create(am_handle **out, int is_f64, const int *nodes, int n_nodes, const 
                     if (kmax > 8192) throw CudaFail{"hidden layers wider than 8192 overflow the int32 digit accumulators"};
                     if (const char *e = getenv("AM_B200_SPLIT_EPI")) h->split_epi = atoi(e);
                     if (h->split_epi != 2 && h->split_epi != 4) h->split_epi = 1;
+                    if (const char *e = getenv("AM_B200_SPLIT_BK")) h->split_bk = (atoi(e) == 32) ? 32 : 64;
                     for_split_digits([&](auto sd) {
                         constexpr int SD = decltype(sd)::value;
                         const int bytes = (int)SplitCfg<SD>::SMEM;
                         CK(cudaFuncSetAttribute(split_gemm_kernel<SD, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
                         CK(cudaFuncSetAttribute(split_gemm_kernel<SD, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
                         CK(cudaFuncSetAttribute(split_gemm_kernel<SD, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                        CK(cudaFuncSetAttribute(split_gemm_kernel<SD, 1, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)SplitCfg<SD, 64>::SMEM));
                     });
                     break;
                 default: prep(GemmDefault{}, compose_gemm_kernel<GemmDefault>); break;

@@ -57,15 +57,17 @@ constexpr int SP_THREADS = 192;    // EW = 1; in general 64 + 128 EW (split_thre
 __host__ __device__ constexpr int split_threads(int ew) { return 64 + 128 * ew; }
 constexpr int SP_KPAD = 32;       // digit rows are padded to a multiple of this many K bytes
 
-template <int SD>
+template <int SD, int BK = SP_BK>      // BK: K bytes per pipeline stage (32 = one kind::i8 instruction, 64 = two)
 struct SplitCfg {
-    static constexpr int STAGE_A = SD * SP_BM * SP_BK;
-    static constexpr int STAGE_B = SD * SP_BN * SP_BK;
+    static constexpr int STAGE_A = SD * SP_BM * BK;
+    static constexpr int STAGE_B = SD * SP_BN * BK;
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr int STAGES = (215 * 1024) / STAGE;
     static constexpr int TMEM_COLS = 512;
     static constexpr int FRAC_BITS = 8 * SD - 2;         // |X| = |x| 2^(FRAC_BITS - e) <= 2^FRAC_BITS
     static constexpr size_t SMEM = size_t(STAGES) * STAGE + 1024 /* alignment slack */ + 2048 /* barriers, tile constants */;
+    static_assert(BK == 32 || BK == 64, "stage depth");
+    static_assert(STAGES >= 2, "the ring needs two stages");
     static_assert(SD * SP_BN <= TMEM_COLS, "accumulators exceed TMEM");
     static_assert(STAGE % 1024 == 0 && STAGE_A % 1024 == 0, "stage bases must keep the swizzle alignment");
 };
@@ -345,11 +347,16 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
-// K-major operand, rows of 32 bytes, SWIZZLE_32B: 8-row groups are 256 B apart (SBO); version 1 (sm_100)
+// K-major operand, rows of BK bytes, SWIZZLE_32B (BK = 32) / SWIZZLE_64B (BK = 64): 8-row groups are 8 BK bytes apart
+// (SBO); version 1 (sm_100).  With BK = 64 the second 32-byte K slab of a row starts 32 B further: the swizzle is a
+// function of the shared-memory address bits, so the descriptor's start address is simply advanced (the row-group bases
+// stay aligned to the 512-byte swizzle period).
+template <int BK = SP_BK>
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr)
 {
-    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(256 >> 4) << 32) | (uint64_t(1) << 46) |
-           (uint64_t(6) << 61);
+    constexpr uint64_t layout = (BK == 32) ? 6 : 4;      // UMMA LayoutType: SWIZZLE_32B = 6, SWIZZLE_64B = 4
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t((8 * BK) >> 4) << 32) | (uint64_t(1) << 46) |
+           (layout << 61);
 }
 // kind::i8 instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t tc_idesc_i8(int n)
@@ -375,7 +382,7 @@ __device__ __forceinline__ void tc_ld_cols(uint32_t taddr, int (&v)[8]) { tc_ld8
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 struct SplitArgs {
-    int k_steps;                // Kpad / 32
+    int k_steps;                // pipeline stages per tile: ceil(Kpad / BK)
     int M, m_tiles, S;          // output neurons, M tiles, state slots of the launch
     int n_tiles;                // tiles of this launch = m_tiles * (state tiles dealt to this chain)
     const int *perm;            // slot -> state
@@ -400,11 +407,11 @@ __device__ __forceinline__ double i32_to_f64(int x)
 // Persistent: gridDim.x CTAs (one per SM) stride over the tiles; the TMA producer runs ahead into the next
 // tile while the epilogue drains TMEM, TMEM / barriers are set up once per CTA.
 // EW: epilogue warps per TMEM lane quarter (1, 2 or 4); CW: accumulator columns per tcgen05.ld chunk (16 or 8)
-template <int SD, int EW = 1, int CW = 16>
+template <int SD, int EW = 1, int CW = 16, int BK = SP_BK>
 __global__ void __launch_bounds__(split_threads(EW), 1)
 split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SplitArgs a)
 {
-    using C = SplitCfg<SD>;
+    using C = SplitCfg<SD, BK>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw0 = smem_u32(smem_raw);
     const uint32_t base = (raw0 + 1023u) & ~1023u;
@@ -457,8 +464,8 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
                     const uint32_t sa = base + stage * C::STAGE, sb = sa + C::STAGE_A;
                     mbar_expect_tx(bar_full + 8 * stage, C::STAGE);
-                    tma_load_3d(sa, &tmA, ks * SP_BK, m0, 0, bar_full + 8 * stage);
-                    tma_load_3d(sb, &tmB, ks * SP_BK, n0, 0, bar_full + 8 * stage);
+                    tma_load_3d(sa, &tmA, ks * BK, m0, 0, bar_full + 8 * stage);
+                    tma_load_3d(sb, &tmB, ks * BK, n0, 0, bar_full + 8 * stage);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -474,15 +481,33 @@ split_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = base + stage * C::STAGE, sb = sa + C::STAGE_A;
+                    if constexpr (BK == SP_BK) {
 #pragma unroll
-                    for (int i = 0; i < SD; ++i) {
-                        const uint64_t adesc = tc_smem_desc(sa + i * (SP_BM * SP_BK));
-                        const int n_total = (SD - i) * SP_BN;
+                        for (int i = 0; i < SD; ++i) {
+                            const uint64_t adesc = tc_smem_desc(sa + i * (SP_BM * SP_BK));
+                            const int n_total = (SD - i) * SP_BN;
 #pragma unroll
-                        for (int c0 = 0; c0 < n_total; c0 += 256) {
-                            const int n = (n_total - c0 < 256) ? (n_total - c0) : 256;
-                            tc_mma_i8(tmem + (uint32_t)(i * SP_BN + c0), adesc, tc_smem_desc(sb + c0 * SP_BK), tc_idesc_i8(n),
-                                      (ks > 0 || i > 0) ? 1u : 0u);
+                            for (int c0 = 0; c0 < n_total; c0 += 256) {
+                                const int n = (n_total - c0 < 256) ? (n_total - c0) : 256;
+                                tc_mma_i8(tmem + (uint32_t)(i * SP_BN + c0), adesc, tc_smem_desc(sb + c0 * SP_BK), tc_idesc_i8(n),
+                                          (ks > 0 || i > 0) ? 1u : 0u);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < BK / SP_BK; ++kk) {    // 32-byte K slabs of the stage
+#pragma unroll
+                            for (int i = 0; i < SD; ++i) {
+                                const uint64_t adesc = tc_smem_desc<BK>(sa + i * (SP_BM * BK) + kk * SP_BK);
+                                const int n_total = (SD - i) * SP_BN;
+#pragma unroll
+                                for (int c0 = 0; c0 < n_total; c0 += 256) {
+                                    const int n = (n_total - c0 < 256) ? (n_total - c0) : 256;
+                                    tc_mma_i8(tmem + (uint32_t)(i * SP_BN + c0), adesc,
+                                              tc_smem_desc<BK>(sb + c0 * BK + kk * SP_BK), tc_idesc_i8(n),
+                                              (ks > 0 || kk > 0 || i > 0) ? 1u : 0u);
+                                }
+                            }
                         }
                     }
                     tc_commit(bar_empty + 8 * stage);                // frees the stage once its MMAs have read it
