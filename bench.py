@@ -86,9 +86,11 @@ def roofline(variant, split_digits, achieved, fp64_peak, launches, ms, flops):
                                "MEASURED_PEAKS.json; tools/fp64_peak.cu: DFMA 37.0, DMMA 37.0, cuBLAS DGEMM 35.8"}
     products = split_digits * (split_digits + 1) // 2
     bf16, src = 1400.0, "fallback of /opt/skills/guides/B200_PROFILING.md (sustained bf16 1.4 PFLOP/s)"
+    burst = None
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         bf16, src = float(mp["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained"
+        burst = float(mp["bf16_tflops"])
     except Exception:
         pass
     peak = 2.0 * bf16 / products
@@ -106,6 +108,9 @@ def roofline(variant, split_digits, achieved, fp64_peak, launches, ms, flops):
             "traffic_source": "scaled from the committed ncu --set full capture (profiles/ncu_traffic.json), not measured in this run",
             "launches": launches, "avg_launch_ms": avg_ms,
             "int8_tops_achieved": achieved * products, "int8_tops_peak": 2.0 * bf16, "digit_products": products,
+            # the sustained bf16 figure is a power-capped cuBLAS run: a fraction near (or above) 1 of the peak derived from
+            # it means "as fast as a power-capped library GEMM", not "at the silicon limit" -- see the two other fractions
+            "frac_of_burst_derived_peak": (achieved / (2.0 * burst / products)) if burst else None,
             "peak_source": f"FP64-equivalent TFLOP/s: algorithmic 2*M*K*4*S flops of the launch; peak = int8 tensor peak / "
                            f"{products} digit products, int8 peak = 2 x {src} ({bf16:.0f})"}
 
