@@ -58,6 +58,30 @@ def test_planes_equal_integer_restatement(name, sd, monkeypatch, oracle_lib):
         assert np.abs(planes[i] - p).max() <= bound * max(1.0, np.abs(p).max()), (name, sd, i, np.abs(planes[i] - p).max())
 
 
+@pytest.mark.parametrize("name,sd", [("mlp3x256s_cube", 7), ("mlp4x128s", 6), ("skipnet", 7)])
+def test_pipeline_variants_of_the_split_gemm_are_bit_identical(name, sd, monkeypatch):
+    """Stage depth (64-byte K slabs with SWIZZLE_64B boxes, the default, vs the 32-byte slabs of rounds 1-2) and the number
+    of epilogue warps per TMEM lane quarter only change how the operands travel and who drains the accumulators: every
+    output is produced by the same instruction sequence, so the rows must agree bit for bit (tools/epi_check.py does the
+    same on the full 8x512 march; profiles/r02_split_bk64.md, r02_split_epilogue_warps.md)."""
+    case = build_case(name)
+    rows = {}
+    for label, env in (("bk64", {"AM_B200_SPLIT_BK": "64"}), ("bk32", {"AM_B200_SPLIT_BK": "32"}),
+                       ("bk32_epi2", {"AM_B200_SPLIT_BK": "32", "AM_B200_SPLIT_EPI": "2"}),
+                       ("bk32_epi4", {"AM_B200_SPLIT_BK": "32", "AM_B200_SPLIT_EPI": "4"})):
+        for k in ("AM_B200_SPLIT_BK", "AM_B200_SPLIT_EPI"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _, planes, equ = _planes(case, 37, sd, monkeypatch)
+        rows[label] = (np.ascontiguousarray(planes).copy(), np.ascontiguousarray(equ).copy())
+    ref_p, ref_e = rows["bk32"]
+    assert np.isfinite(ref_p).all() and np.abs(ref_p).max() > 0
+    for label, (p, e) in rows.items():
+        assert np.array_equal(p.view(np.uint64), ref_p.view(np.uint64)), label
+        assert np.array_equal(e.view(np.uint64), ref_e.view(np.uint64)), label
+
+
 @pytest.mark.parametrize("name", ["skipnet", "chair", "mlp4x128s", "mlp3x256s_cube"])
 def test_region_set_and_loops_match_oracle(oracle_lib, name):
     case = build_case(name)
