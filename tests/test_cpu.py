@@ -423,3 +423,25 @@ def test_split_gemm_restatement_matches_fp64_reference(oracle_lib):
         scale = np.abs(p).max(axis=0)
         scale[scale == 0] = 1.0
         assert (np.abs(p - q) / scale).max() < 1e-14
+
+
+def test_bench_roofline_objects_carry_the_contract_keys():
+    """bench.py's roofline object for both composition paths: bound / achieved / peak / unit / frac / traffic, the
+    fractions consistent with the peaks they name (no GPU needed: pure arithmetic on the committed peak files)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    r = bench.roofline(2, 7, 90.0, 37.0, 1928, 1300.0, 90.0e12 * 1.3)
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "launches", "avg_launch_ms"):
+        assert k in r, k
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["digit_products"] == 28
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["int8_tops_achieved"] - 28 * r["achieved"]) < 1e-9
+    if r["instruction_peak"] is not None:       # profiles/r02_int8_peak.json is committed
+        assert abs(r["instruction_peak"]["frac_of_instruction_peak"] -
+                   r["int8_tops_achieved"] / r["instruction_peak"]["int8_tops_instruction_peak"]) < 1e-12
+        assert r["instruction_peak"]["frac_of_instruction_peak"] < r["frac"]
+    d = bench.roofline(0, 7, 30.0, 37.0, 100, 50.0, 30.0e12 * 0.05)
+    assert d["bound"] == "fp64" and abs(d["frac"] - 30.0 / 37.0) < 1e-12
+    assert bench.flops_per_face([3] + [512] * 8 + [1]) == 14684160        # SURVEY 8(d)
